@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- patch-view NCC evals/s (and refined patches/s) of the PMVS photometric path.
+
+A "step" is one pass of the hot path over one batch of synthetic seed patches:
+Seed::FilterPatches (FilterByErrorMeasurement for every seed) followed by
+Seed::OptimizePatches (Nelder-Mead refinement of every survivor), i.e.
+Seed::OptimizeAndRefinePatches (reference methods/pmvs/seed.cpp:88-144).
+
+Workload (N=1): BASELINE.json configs[1] -- synthetic textured sphere, 16 views
+1280x960, ~1M seed patches, cell_size (mu) = 7.  N>1: every rank gets its own
+1M-seed shard of the same scene (weak scaling, no data-path collective).
+
+  value  = patch-view evals/s with the seeds resident in HBM (dp_*_dev entry points)
+  e2e    = the same through the host-buffer C ABI (dp_filter + dp_refine on pinned host
+           arrays, H2D/D2H inside the timed region)
+  roofline = the refine kernel against the measured HBM copy bandwidth
+  cpu_baseline = the CPU oracle (OpenMP, all host threads) on a bounded sample
+
+`--impl reference` times the CPU oracle alone (the reference C++ cannot be built here:
+no OpenCV/Eigen/PCL headers).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CELL = 7
+METRIC = "patch_view_ncc_evals_per_s"
+UNIT = "evals/s"
+
+
+def b_alg(s, nv):
+    """Algorithmic bytes per patch-view eval (SURVEY 8d / BASELINE.md section 3)."""
+    return 3.0 * (2 * (s // 2) + 2) ** 2 + 4.0 + (28.0 + 2.0 * nv) / max(nv, 1)
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True,
+                                     timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for nm, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def make_workload(n_seeds, rank=0, small=False):
+    from densepoints_b200 import scenes
+    if small:
+        sc = scenes.make_sphere_scene(seed=2, n_views=16, width=640, height=480, f=500.0)
+    else:
+        sc = scenes.make_sphere_scene(seed=2, n_views=16, width=1280, height=960, f=1000.0)
+    seeds = scenes.make_seeds(sc, n_seeds, seed=200 + rank)
+    return sc, seeds
+
+
+def run_reference(args):
+    """CPU arm: the oracle's restatement of the reference path on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    orc.build()
+    orc.set_homography_mode(0)           # the OpenCV procedure (findHomography's eigen-solve)
+    sample = args.cpu_sample
+    sc, seeds = make_workload(sample, small=args.small)
+    V = orc.Views(sc.P, sc.images)
+    nvis, vis, _, _ = orc.visibility_batch(V, seeds["pos"], seeds["nrm"], seeds["ref"])
+    prm = orc.default_params()
+
+    def step():
+        keep, fnvis, fvis = orc.filter_batch(V, seeds["pos"], seeds["nrm"], seeds["ref"], nvis, vis,
+                                             CELL, prm.score_threshold, prm.minimum_visible_image)
+        m = keep.astype(bool)
+        pos, nrm, fc, _ = orc.refine_batch(V, seeds["pos"][m], seeds["nrm"][m], seeds["ref"][m],
+                                           fnvis[m], fvis[m], CELL, prm)
+        return int(nvis.sum()) + int((fc.astype(np.int64) * fnvis[m]).sum()), int(m.sum())
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    evals = refined = 0
+    for _ in range(args.steps):
+        e, r = step()
+        evals += e
+        refined += r
+    dt = time.perf_counter() - t0
+    val = evals / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64",
+            "data": "synthetic", "refined_patches_per_s": refined / dt,
+            "config": {"workload": workload_name(args), "cell_size": CELL,
+                       "sample_seeds_per_step": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+                             "sample": f"{sample} seeds of the same scene per step: filter + refine "
+                                       "with the CPU oracle (OpenMP, OpenCV-style DLT homography)"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    if args.small:
+        return "reduced: textured sphere, 16 views 640x480, seed filter+refine, mu=7"
+    return ("BASELINE configs[1]: synthetic textured sphere, 16 views 1280x960, "
+            f"{args.seeds} seed patches per GPU, Seed::FilterPatches + OptimizePatches, mu=7")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--seeds", type=int, default=1 << 20)
+    ap.add_argument("--cpu-sample", type=int, default=3072)
+    ap.add_argument("--small", action="store_true", help="reduced scene/seed count (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.small and args.seeds == 1 << 20:
+        args.seeds = 1 << 15
+    if args.warmup < 3:
+        args.warmup = 3            # timing rule: W >= 3
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from densepoints_b200 import build as dpbuild
+    from densepoints_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the CUDA path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    dpbuild.build_cuda()
+
+    sc, seeds = make_workload(args.seeds, rank=rank, small=args.small)
+    ctx = capi.Context(local_rank)
+    ctx.set_views(sc.P, sc.images)
+    prm = ctx.get_params()
+    n, V = args.seeds, sc.n_views
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # ---- resident inputs (HBM) --------------------------------------------------------------
+    def dev_t(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    pos0, nrm0 = dev_t(seeds["pos"]), dev_t(seeds["nrm"])
+    ref = dev_t(seeds["ref"].astype(np.int32))
+    nvis0 = torch.zeros(n, dtype=torch.int32, device=dev)
+    vis0 = torch.full((n, V), -1, dtype=torch.int32, device=dev)
+    b0 = capi.dev_batch(n, V, pos0.data_ptr(), nrm0.data_ptr(), ref.data_ptr(), nvis0.data_ptr(),
+                        vis0.data_ptr())
+    ctx.visibility_dev(b0, stream=stream)           # Patch::InitRelatedImages (setup, untimed)
+    torch.cuda.synchronize()
+    pos, nrm, nvis, vis = (torch.empty_like(t) for t in (pos0, nrm0, nvis0, vis0))
+    keep = torch.zeros(n, dtype=torch.uint8, device=dev)
+    evals = torch.zeros(n, dtype=torch.int32, device=dev)
+    wb = capi.dev_batch(n, V, pos.data_ptr(), nrm.data_ptr(), ref.data_ptr(), nvis.data_ptr(),
+                        vis.data_ptr())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    refine_ms = []
+
+    def step_resident(record=False):
+        flush.zero_()                                   # L2 flush between iterations
+        pos.copy_(pos0); nrm.copy_(nrm0); nvis.copy_(nvis0); vis.copy_(vis0)
+        ctx.filter_dev(wb, CELL, keep.data_ptr(), stream=stream)
+        if record:
+            ev[0].record()
+        ctx.refine_dev(wb, CELL, mask_ptr=keep.data_ptr(), evals_ptr=evals.data_ptr(),
+                       stream=stream)
+        if record:
+            ev[1].record()
+            ev[1].synchronize()
+            refine_ms.append(ev[0].elapsed_time(ev[1]))
+
+    def count_evals():
+        e_filter = int(nvis0.sum().item())
+        e_refine = int((evals.to(torch.int64) * nvis.to(torch.int64) * keep.to(torch.int64)).sum().item())
+        return e_filter, e_refine, int(keep.sum().item())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    torch.cuda.synchronize()
+    e_filter, e_refine, n_refined = count_evals()
+    evals_per_step = e_filter + e_refine
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctx.launch_count()
+    barrier()
+    ev[2].record()
+    for _ in range(args.steps):
+        step_resident(record=True)
+    ev[3].record()
+    barrier()
+    gpu_ms = ev[2].elapsed_time(ev[3])
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop()
+
+    t_ms = torch.tensor([gpu_ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(evals_per_step), float(n_refined)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    max_ms = float(t_ms.item())
+    value = float(tot[0].item()) * args.steps / (max_ms * 1e-3)
+    refined_per_s = float(tot[1].item()) * args.steps / (max_ms * 1e-3)
+
+    # ---- e2e: the host-buffer C ABI on pinned host arrays ---------------------------------------
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t, t.numpy()
+    nvis_h0 = nvis0.cpu().numpy()
+    vis_h0 = vis0.cpu().numpy()
+    hold = [pinned(x) for x in (seeds["pos"], seeds["nrm"], seeds["ref"].astype(np.int32), nvis_h0,
+                                vis_h0)]
+    h_pos, h_nrm, h_ref, h_nvis, h_vis = (h[1] for h in hold)
+
+    def step_e2e():
+        # what methods/pmvs would do through the drop-in: FilterPatches -> RemovePatches ->
+        # OptimizePatches, every call moving its host arrays in and its results out
+        k, fnvis, fvis = ctx.filter(h_pos, h_nrm, h_ref, h_nvis, h_vis, CELL)
+        m = k.astype(bool)
+        p2, n2, ev2, _ = ctx.refine(h_pos[m], h_nrm[m], h_ref[m], fnvis[m], fvis[m], CELL)
+        return int(h_nvis.sum()) + int((ev2.astype(np.int64) * fnvis[m]).sum()), int(m.sum())
+
+    e2e_steps = max(1, min(args.steps, 2))
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_evals = 0
+    for _ in range(e2e_steps):
+        e, _r = step_e2e()
+        e2e_evals += e
+    barrier()
+    e2e_dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    e2e_ev = torch.tensor([float(e2e_evals)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e_ev, op=dist.ReduceOp.SUM)
+    e2e_value = float(e2e_ev.item()) / float(e2e_dt.item())
+    n_keep = int(keep.sum().item())
+    h2d = n * (12 + 12 + 4 + 4 + 4 * V) + n_keep * (12 + 12 + 4 + 4 + 4 * V)
+    d2h = n * (1 + 4 + 4 * V) + n_keep * (12 + 12 + 4 + 24)
+
+    # ---- roofline of the dominant kernel (refine) ------------------------------------------------
+    mean_nv = float((nvis.to(torch.float64) * keep).sum().item() / max(n_keep, 1))
+    refine_kernel_ms = float(np.mean(refine_ms))
+    alg_bytes = e_refine * b_alg(CELL, mean_nv)
+    peak, peak_src = hbm_peak()
+    achieved = alg_bytes / (refine_kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "kernel": "dp_refine_kernel<2>",
+                "kernel_ms": refine_kernel_ms, "peak_source": peak_src,
+                "alg_bytes_per_eval": b_alg(CELL, mean_nv),
+                "share_of_step": refine_kernel_ms * args.steps / gpu_ms,
+                "note": "issue-bound gather/reduce (~1.7k ops per eval): the image set (79 MB "
+                        "BGRx) is L2-resident, so HBM is not the binding roof"}
+
+    # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as orc
+        orc.build()
+        orc.set_homography_mode(0)
+        ns = min(args.cpu_sample, n)
+        OV = orc.Views(sc.P, sc.images)
+        oprm = orc.default_params()
+        t0 = time.perf_counter()
+        k, fnv, fv = orc.filter_batch(OV, h_pos[:ns], h_nrm[:ns], h_ref[:ns], h_nvis[:ns],
+                                      h_vis[:ns], CELL, oprm.score_threshold,
+                                      oprm.minimum_visible_image)
+        m = k.astype(bool)
+        _, _, fc, _ = orc.refine_batch(OV, h_pos[:ns][m], h_nrm[:ns][m], h_ref[:ns][m], fnv[m],
+                                       fv[m], CELL, oprm)
+        dt = time.perf_counter() - t0
+        cpu_evals = int(h_nvis[:ns].sum()) + int((fc.astype(np.int64) * fnv[m]).sum())
+        cpu = {"value": cpu_evals / dt, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+               "sample": f"first {ns} seeds of the same workload, filter + refine, CPU oracle "
+                         f"(OpenMP); {dt:.1f} s",
+               "refined_patches_per_s": float(m.sum()) / dt}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": max_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8/f64", "data": "synthetic",
+                "refined_patches_per_s": refined_per_s,
+                "evals_per_refined_patch": e_refine / max(n_refined, 1) / max(mean_nv, 1e-9),
+                "mean_visible_views": mean_nv,
+                "config": {"workload": workload_name(args), "cell_size": CELL,
+                           "seeds_per_gpu": n, "views": V,
+                           "l2": "256 MB buffer written between iterations (L2 flush), inside the "
+                                 "timed region"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+                "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,620 @@
+// densepoints_cuda.cu -- C ABI (include/densepoints_cuda.h) over the sm_100a kernels.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "dp_aux_kernels.cuh"
+#include "dp_context.h"
+#include "dp_kernels.cuh"
+
+// ---------------------------------------------------------------------------------------
+// helpers
+
+int dp_fail(dp_context *ctx, int code, const char *what, cudaError_t e) {
+  if (ctx) {
+    ctx->err = what ? what : "error";
+    if (e != cudaSuccess) {
+      ctx->err += ": ";
+      ctx->err += cudaGetErrorString(e);
+    }
+  }
+  return code;
+}
+
+static int npass_for(int s) {
+  int npx = s * s;
+  int np = (npx + 31) / 32;
+  int p = 1;
+  while (p < np) p <<= 1;
+  return p;
+}
+
+extern "C" void dp_default_params(dp_params *p) {
+  if (!p) return;
+  p->score_threshold = 0.6;
+  p->minimum_visible_image = 3;
+  p->visible_threshold = 0.78;
+  p->candidate_threshold = 1.04;
+  p->grid_scale = 8;
+  p->max_patches_per_cell = 1;
+  p->nm_step[0] = 0.02;
+  p->nm_step[1] = 0.2;
+  p->nm_step[2] = 0.2;
+  p->nm_max_evals = 500;
+  p->nm_eps = 0.0001;
+  p->max_pops = 10000000LL;
+}
+
+extern "C" int dp_abi_version(void) { return DP_ABI_VERSION; }
+
+static int check_params(dp_context *ctx, const dp_params *p) {
+  if (p->grid_scale <= 0) return dp_fail(ctx, DP_ERR_INVALID_ARG, "grid_scale must be > 0");
+  if (p->max_patches_per_cell != 1)
+    return dp_fail(ctx, DP_ERR_INVALID_ARG, "only max_patches_per_cell == 1 is supported");
+  if (p->nm_max_evals < 4) return dp_fail(ctx, DP_ERR_INVALID_ARG, "nm_max_evals must be >= 4");
+  return DP_OK;
+}
+
+extern "C" int dp_create(dp_context **out, int device, const dp_params *params) {
+  if (!out) return DP_ERR_INVALID_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return DP_ERR_NO_DEVICE;
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) return DP_ERR_NO_DEVICE;
+  }
+  if (device >= count) return DP_ERR_NO_DEVICE;
+  if (cudaSetDevice(device) != cudaSuccess) return DP_ERR_CUDA;
+  dp_context *ctx = new dp_context();
+  ctx->device = device;
+  if (params)
+    ctx->prm = *params;
+  else
+    dp_default_params(&ctx->prm);
+  if (check_params(ctx, &ctx->prm) != DP_OK) {
+    delete ctx;
+    return DP_ERR_INVALID_ARG;
+  }
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return DP_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  *out = ctx;
+  return DP_OK;
+}
+
+static void free_views(dp_context *ctx) {
+  for (auto &v : ctx->views)
+    for (auto &l : v.levels)
+      if (l.img) cudaFree(l.img);
+  ctx->views.clear();
+  ctx->views_dirty = true;
+}
+
+extern "C" void dp_destroy(dp_context *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  free_views(ctx);
+  DpDevBuf *bufs[] = {&ctx->d_views, &ctx->s_pos, &ctx->s_nrm, &ctx->s_ref, &ctx->s_nvis,
+                      &ctx->s_vis, &ctx->s_rgb, &ctx->s_ncc, &ctx->s_tex, &ctx->s_valid,
+                      &ctx->s_keep, &ctx->s_evals, &ctx->s_xbest, &ctx->s_cand, &ctx->s_ncand,
+                      &ctx->s_img, &ctx->s_misc, &ctx->work_counter, &ctx->e_pos, &ctx->e_nrm,
+                      &ctx->e_ref, &ctx->e_nvis, &ctx->e_vis, &ctx->e_keep, &ctx->e_seq,
+                      &ctx->e_cells, &ctx->e_flags, &ctx->e_scan, &ctx->e_count, &ctx->org.grid,
+                      &ctx->org.claim, &ctx->org.pos, &ctx->org.nrm, &ctx->org.rgb, &ctx->org.ref,
+                      &ctx->org.nvis, &ctx->org.vis};
+  for (DpDevBuf *b : bufs) b->release();
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char *dp_last_error(const dp_context *ctx) {
+  return ctx ? ctx->err.c_str() : "null context";
+}
+
+extern "C" int dp_set_params(dp_context *ctx, const dp_params *p) {
+  if (!ctx || !p) return DP_ERR_INVALID_ARG;
+  int rc = check_params(ctx, p);
+  if (rc != DP_OK) return rc;
+  if (p->grid_scale != ctx->prm.grid_scale) {
+    ctx->views_dirty = true;
+    ctx->org.ready = false;
+  }
+  ctx->prm = *p;
+  return DP_OK;
+}
+
+extern "C" int dp_get_params(const dp_context *ctx, dp_params *p) {
+  if (!ctx || !p) return DP_ERR_INVALID_ARG;
+  *p = ctx->prm;
+  return DP_OK;
+}
+
+extern "C" int dp_sync(dp_context *ctx) {
+  if (!ctx) return DP_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  DP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return DP_OK;
+}
+
+extern "C" int64_t dp_launch_count(const dp_context *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------------------------------
+// views
+
+// View::SetProjectionMatrix (core/types.cpp:28-68): camera centre (null vector of P) and the
+// orthogonal factor of the RQ decomposition of P[:, :3] with a positive-diagonal K; only its
+// first row (View::GetXAxis) is needed on the path.
+static void decompose_projection(const double P[12], double xaxis[3], double center[3]) {
+  const double m00 = P[0], m01 = P[1], m02 = P[2], m10 = P[4], m11 = P[5], m12 = P[6],
+               m20 = P[8], m21 = P[9], m22 = P[10];
+  const double b0 = -P[3], b1 = -P[7], b2 = -P[11];
+  // Cramer: M c = b
+  const double c00 = m11 * m22 - m12 * m21, c01 = m12 * m20 - m10 * m22, c02 = m10 * m21 - m11 * m20;
+  const double det = m00 * c00 + m01 * c01 + m02 * c02;
+  const double c10 = m02 * m21 - m01 * m22, c11 = m00 * m22 - m02 * m20, c12 = m01 * m20 - m00 * m21;
+  const double c20 = m01 * m12 - m02 * m11, c21 = m02 * m10 - m00 * m12, c22 = m00 * m11 - m01 * m10;
+  center[0] = (c00 * b0 + c10 * b1 + c20 * b2) / det;
+  center[1] = (c01 * b0 + c11 * b1 + c21 * b2) / det;
+  center[2] = (c02 * b0 + c12 * b1 + c22 * b2) / det;
+  // Gram-Schmidt from the last row up: r2 = m2/|m2|, r1 _|_ r2, r0 _|_ r1, r2
+  double r2[3] = {m20, m21, m22};
+  double n2 = sqrt(r2[0] * r2[0] + r2[1] * r2[1] + r2[2] * r2[2]);
+  for (double &v : r2) v /= n2;
+  double r1[3] = {m10, m11, m12};
+  double d12 = r1[0] * r2[0] + r1[1] * r2[1] + r1[2] * r2[2];
+  for (int j = 0; j < 3; ++j) r1[j] -= d12 * r2[j];
+  double n1 = sqrt(r1[0] * r1[0] + r1[1] * r1[1] + r1[2] * r1[2]);
+  for (double &v : r1) v /= n1;
+  double r0[3] = {m00, m01, m02};
+  double d02 = r0[0] * r2[0] + r0[1] * r2[1] + r0[2] * r2[2];
+  double d01 = r0[0] * r1[0] + r0[1] * r1[1] + r0[2] * r1[2];
+  for (int j = 0; j < 3; ++j) r0[j] -= d02 * r2[j] + d01 * r1[j];
+  double n0 = sqrt(r0[0] * r0[0] + r0[1] * r0[1] + r0[2] * r0[2]);
+  for (int j = 0; j < 3; ++j) xaxis[j] = r0[j] / n0;
+}
+
+extern "C" int dp_set_num_views(dp_context *ctx, int n_views) {
+  if (!ctx || n_views < 0 || n_views > 65535) return dp_fail(ctx, DP_ERR_INVALID_ARG, "n_views");
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  free_views(ctx);
+  ctx->views.resize(n_views);
+  ctx->n_levels = 1;
+  ctx->level = 0;
+  ctx->org.ready = false;
+  return DP_OK;
+}
+
+extern "C" int dp_num_views(const dp_context *ctx) { return ctx ? (int)ctx->views.size() : 0; }
+
+extern "C" int dp_upload_view(dp_context *ctx, int view_id, const double P[12], const double *xaxis,
+                              const double *center, const uint8_t *bgr, int width, int height,
+                              size_t stride) {
+  if (!ctx) return DP_ERR_INVALID_ARG;
+  if (view_id < 0 || view_id >= (int)ctx->views.size())
+    return dp_fail(ctx, DP_ERR_INVALID_ARG, "view_id out of range (call dp_set_num_views)");
+  if (!P || !bgr || width <= 0 || height <= 0 || stride < (size_t)width * 3)
+    return dp_fail(ctx, DP_ERR_INVALID_ARG, "dp_upload_view arguments");
+  cudaSetDevice(ctx->device);
+  DpViewHost &v = ctx->views[view_id];
+  for (auto &l : v.levels)
+    if (l.img) cudaFree(l.img);
+  v.levels.clear();
+  memcpy(v.P, P, sizeof(double) * 12);
+  double xa[3], c[3];
+  decompose_projection(P, xa, c);
+  for (int j = 0; j < 3; ++j) {
+    v.xaxis[j] = xaxis ? xaxis[j] : xa[j];
+    v.center[j] = center ? center[j] : c[j];
+  }
+  DpLevel l;
+  l.width = width;
+  l.height = height;
+  l.pitch_px = (width + 31) & ~31;  // 128-byte aligned rows
+  DP_CUDA(ctx, cudaMalloc(&l.img, (size_t)l.pitch_px * height * sizeof(uint32_t)));
+  v.levels.push_back(l);
+  const size_t bytes = stride * (size_t)height;
+  DP_CUDA(ctx, ctx->s_img.ensure(bytes));
+  DP_CUDA(ctx, cudaMemcpyAsync(ctx->s_img.ptr, bgr, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  dim3 grid((l.pitch_px + 255) / 256, height);
+  dp_pack_bgrx_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->s_img.as<uint8_t>(), stride, width,
+                                                      height, l.img, l.pitch_px);
+  ++ctx->launches;
+  DP_CUDA(ctx, cudaGetLastError());
+  DP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  v.set = true;
+  ctx->views_dirty = true;
+  ctx->org.ready = false;
+  return DP_OK;
+}
+
+extern "C" int dp_get_view(const dp_context *ctx, int view_id, double xaxis[3], double center[3],
+                           int *width, int *height) {
+  if (!ctx || view_id < 0 || view_id >= (int)ctx->views.size() || !ctx->views[view_id].set)
+    return DP_ERR_INVALID_ARG;
+  const DpViewHost &v = ctx->views[view_id];
+  const DpLevel &l = v.levels[std::min<int>(ctx->level, (int)v.levels.size() - 1)];
+  for (int j = 0; j < 3; ++j) {
+    if (xaxis) xaxis[j] = v.xaxis[j];
+    if (center) center[j] = v.center[j];
+  }
+  if (width) *width = l.width;
+  if (height) *height = l.height;
+  return DP_OK;
+}
+
+// Builds the device view table for the active pyramid level.  Level l uses
+// P_l = diag(2^-l, 2^-l, 1) P (exact scaling by a power of two).
+int dp_sync_views(dp_context *ctx) {
+  if (!ctx->views_dirty) return DP_OK;
+  const int nv = (int)ctx->views.size();
+  if (nv == 0) return dp_fail(ctx, DP_ERR_STATE, "no views uploaded");
+  std::vector<DpViewDev> h(nv);
+  long long off = 0;
+  for (int i = 0; i < nv; ++i) {
+    const DpViewHost &v = ctx->views[i];
+    if (!v.set) return dp_fail(ctx, DP_ERR_STATE, "a view was not uploaded");
+    if (ctx->level >= (int)v.levels.size())
+      return dp_fail(ctx, DP_ERR_STATE, "pyramid level not built");
+    const DpLevel &l = v.levels[ctx->level];
+    const double sc = ldexp(1.0, -ctx->level);
+    for (int j = 0; j < 12; ++j) h[i].P[j] = (j < 8) ? v.P[j] * sc : v.P[j];
+    const double n = sqrt(v.xaxis[0] * v.xaxis[0] + v.xaxis[1] * v.xaxis[1] + v.xaxis[2] * v.xaxis[2]);
+    for (int j = 0; j < 3; ++j) {
+      h[i].xa[j] = v.xaxis[j] / n;  // .normalized(), patch.cpp:95
+      h[i].center[j] = v.center[j];
+    }
+    h[i].img = l.img;
+    h[i].width = l.width;
+    h[i].height = l.height;
+    h[i].pitch_px = l.pitch_px;
+    h[i].gw = l.width / ctx->prm.grid_scale;   // patch_organizer.cpp:35-36
+    h[i].gh = l.height / ctx->prm.grid_scale;
+    h[i].grid_off = off;
+    off += (long long)h[i].gw * h[i].gh;
+  }
+  DP_CUDA(ctx, ctx->d_views.ensure(sizeof(DpViewDev) * nv));
+  DP_CUDA(ctx, cudaMemcpyAsync(ctx->d_views.ptr, h.data(), sizeof(DpViewDev) * nv,
+                               cudaMemcpyHostToDevice, ctx->stream));
+  DP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->org.n_cells = off;
+  ctx->views_dirty = false;
+  return DP_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// device-pointer layer
+
+static int check_patch_dev(dp_context *ctx, const dp_patch_dev *p, int cell_size) {
+  if (!ctx || !p) return DP_ERR_INVALID_ARG;
+  if (p->n < 0 || p->vstride <= 0) return dp_fail(ctx, DP_ERR_INVALID_ARG, "patch batch shape");
+  if (cell_size < 2 || cell_size > DP_MAX_CELL_SIZE)
+    return dp_fail(ctx, DP_ERR_INVALID_ARG, "cell_size must be in [2, 32]");
+  if (p->n > 0 && (!p->pos || !p->nrm || !p->ref || !p->nvis || !p->vis))
+    return dp_fail(ctx, DP_ERR_INVALID_ARG, "null patch array");
+  return DP_OK;
+}
+
+static DpPatchArgs patch_args(dp_context *ctx, const dp_patch_dev *p, int s) {
+  DpPatchArgs a;
+  a.views = ctx->d_views.as<DpViewDev>();
+  a.n_views = (int)ctx->views.size();
+  a.n = p->n;
+  a.vstride = p->vstride;
+  a.pos = p->pos;
+  a.nrm = p->nrm;
+  a.ref = p->ref;
+  a.nvis = p->nvis;
+  a.vis = p->vis;
+  a.s = s;
+  return a;
+}
+
+template <bool TEX, bool FILT>
+static void launch_score(const DpScoreArgs &a, int npass, cudaStream_t st) {
+  const unsigned grid = (unsigned)((a.p.n + DP_WARPS - 1) / DP_WARPS);
+  switch (npass) {
+    case 1: dp_score_kernel<1, TEX, FILT><<<grid, DP_WARPS * 32, 0, st>>>(a); break;
+    case 2: dp_score_kernel<2, TEX, FILT><<<grid, DP_WARPS * 32, 0, st>>>(a); break;
+    case 4: dp_score_kernel<4, TEX, FILT><<<grid, DP_WARPS * 32, 0, st>>>(a); break;
+    case 8: dp_score_kernel<8, TEX, FILT><<<grid, DP_WARPS * 32, 0, st>>>(a); break;
+    case 16: dp_score_kernel<16, TEX, FILT><<<grid, DP_WARPS * 32, 0, st>>>(a); break;
+    default: dp_score_kernel<32, TEX, FILT><<<grid, DP_WARPS * 32, 0, st>>>(a); break;
+  }
+}
+
+extern "C" int dp_score_dev(dp_context *ctx, const dp_patch_dev *p, int cell_size, float *ncc,
+                            uint8_t *tex, uint8_t *valid, void *stream) {
+  int rc = check_patch_dev(ctx, p, cell_size);
+  if (rc != DP_OK) return rc;
+  if (p->n == 0) return DP_OK;
+  cudaSetDevice(ctx->device);
+  if ((rc = dp_sync_views(ctx)) != DP_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  DpScoreArgs a;
+  a.p = patch_args(ctx, p, cell_size);
+  a.ncc = ncc;
+  a.tex = tex;
+  a.valid = valid;
+  a.thr = 0;
+  a.min_visible = 0;
+  a.keep = nullptr;
+  const int np = npass_for(cell_size);
+  if (ncc) DP_CUDA(ctx, cudaMemsetAsync(ncc, 0, sizeof(float) * (size_t)p->n * p->vstride, st));
+  if (valid) DP_CUDA(ctx, cudaMemsetAsync(valid, 0, (size_t)p->n * p->vstride, st));
+  if (tex) {
+    DP_CUDA(ctx, cudaMemsetAsync(tex, 0, (size_t)p->n * p->vstride * cell_size * cell_size * 3, st));
+    launch_score<true, false>(a, np, st);
+  } else {
+    launch_score<false, false>(a, np, st);
+  }
+  ++ctx->launches;
+  DP_CUDA(ctx, cudaGetLastError());
+  return DP_OK;
+}
+
+extern "C" int dp_filter_dev(dp_context *ctx, dp_patch_dev *p, int cell_size, uint8_t *keep,
+                             void *stream) {
+  int rc = check_patch_dev(ctx, p, cell_size);
+  if (rc != DP_OK) return rc;
+  if (!keep) return dp_fail(ctx, DP_ERR_INVALID_ARG, "keep is null");
+  if (p->n == 0) return DP_OK;
+  cudaSetDevice(ctx->device);
+  if ((rc = dp_sync_views(ctx)) != DP_OK) return rc;
+  DpScoreArgs a;
+  a.p = patch_args(ctx, p, cell_size);
+  a.ncc = nullptr;
+  a.tex = nullptr;
+  a.valid = nullptr;
+  a.thr = ctx->prm.score_threshold;
+  a.min_visible = ctx->prm.minimum_visible_image;
+  a.keep = keep;
+  launch_score<false, true>(a, npass_for(cell_size), (cudaStream_t)stream);
+  ++ctx->launches;
+  DP_CUDA(ctx, cudaGetLastError());
+  return DP_OK;
+}
+
+template <int NPASS>
+static cudaError_t launch_refine(const DpRefineArgs &a, int sm_count, cudaStream_t st) {
+  int per_sm = 1;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dp_refine_kernel<NPASS>,
+                                                                DP_WARPS * 32, 0);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  long long want = ((long long)a.p.n + DP_WARPS - 1) / DP_WARPS;
+  long long grid = std::min<long long>(want, (long long)sm_count * per_sm);
+  dp_refine_kernel<NPASS><<<(unsigned)grid, DP_WARPS * 32, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+extern "C" int dp_refine_dev(dp_context *ctx, dp_patch_dev *p, int cell_size, const uint8_t *mask,
+                             int32_t *evals, double *xbest, void *stream) {
+  int rc = check_patch_dev(ctx, p, cell_size);
+  if (rc != DP_OK) return rc;
+  if (p->n == 0) return DP_OK;
+  cudaSetDevice(ctx->device);
+  if ((rc = dp_sync_views(ctx)) != DP_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  DP_CUDA(ctx, ctx->work_counter.ensure(sizeof(unsigned int)));
+  DP_CUDA(ctx, cudaMemsetAsync(ctx->work_counter.ptr, 0, sizeof(unsigned int), st));
+  DpRefineArgs a;
+  a.p = patch_args(ctx, p, cell_size);
+  a.evals = evals;
+  a.xbest = xbest;
+  for (int j = 0; j < 3; ++j) a.step[j] = ctx->prm.nm_step[j];
+  a.max_evals = ctx->prm.nm_max_evals;
+  a.eps = ctx->prm.nm_eps;
+  a.work_counter = ctx->work_counter.as<unsigned int>();
+  a.mask = mask;
+  cudaError_t e;
+  switch (npass_for(cell_size)) {
+    case 1: e = launch_refine<1>(a, ctx->sm_count, st); break;
+    case 2: e = launch_refine<2>(a, ctx->sm_count, st); break;
+    case 4: e = launch_refine<4>(a, ctx->sm_count, st); break;
+    case 8: e = launch_refine<8>(a, ctx->sm_count, st); break;
+    case 16: e = launch_refine<16>(a, ctx->sm_count, st); break;
+    default: e = launch_refine<32>(a, ctx->sm_count, st); break;
+  }
+  ++ctx->launches;
+  DP_CUDA(ctx, e);
+  return DP_OK;
+}
+
+extern "C" int dp_visibility_dev(dp_context *ctx, dp_patch_dev *p, int32_t *ncand, int32_t *cand,
+                                 void *stream) {
+  if (!ctx || !p) return DP_ERR_INVALID_ARG;
+  if (p->n < 0 || p->vstride <= 0) return dp_fail(ctx, DP_ERR_INVALID_ARG, "patch batch shape");
+  if (p->n == 0) return DP_OK;
+  if (!p->pos || !p->nrm || !p->ref || !p->nvis || !p->vis)
+    return dp_fail(ctx, DP_ERR_INVALID_ARG, "null patch array");
+  cudaSetDevice(ctx->device);
+  int rc = dp_sync_views(ctx);
+  if (rc != DP_OK) return rc;
+  const long long threads = (long long)p->n * 32;
+  dp_visibility_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      ctx->d_views.as<DpViewDev>(), (int)ctx->views.size(), p->n, p->pos, p->nrm, p->ref,
+      ctx->prm.visible_threshold, ctx->prm.candidate_threshold, p->nvis, p->vis, ncand, cand,
+      p->vstride);
+  ++ctx->launches;
+  DP_CUDA(ctx, cudaGetLastError());
+  return DP_OK;
+}
+
+extern "C" int dp_color_dev(dp_context *ctx, dp_patch_dev *p, void *stream) {
+  if (!ctx || !p) return DP_ERR_INVALID_ARG;
+  if (p->n == 0) return DP_OK;
+  if (p->n < 0 || !p->pos || !p->rgb) return dp_fail(ctx, DP_ERR_INVALID_ARG, "dp_color arguments");
+  cudaSetDevice(ctx->device);
+  int rc = dp_sync_views(ctx);
+  if (rc != DP_OK) return rc;
+  const long long threads = (long long)p->n * 32;
+  dp_color_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      ctx->d_views.as<DpViewDev>(), (int)ctx->views.size(), p->n, p->pos, p->rgb);
+  ++ctx->launches;
+  DP_CUDA(ctx, cudaGetLastError());
+  return DP_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// host-buffer layer: H2D -> kernel -> D2H, synchronous
+
+struct HostBatch {
+  dp_patch_dev d;
+};
+
+static int upload_patches(dp_context *ctx, const dp_patch_soa *h, dp_patch_dev *d, bool need_vis) {
+  if (!h) return DP_ERR_INVALID_ARG;
+  if (h->n < 0 || h->vstride <= 0) return dp_fail(ctx, DP_ERR_INVALID_ARG, "patch batch shape");
+  if (h->n > 0 && (!h->pos || !h->nrm || !h->ref || !h->nvis || !h->vis))
+    return dp_fail(ctx, DP_ERR_INVALID_ARG, "null patch array");
+  cudaSetDevice(ctx->device);
+  const size_t n = (size_t)h->n, vs = (size_t)h->vstride;
+  DP_CUDA(ctx, ctx->s_pos.ensure(n * 12));
+  DP_CUDA(ctx, ctx->s_nrm.ensure(n * 12));
+  DP_CUDA(ctx, ctx->s_ref.ensure(n * 4));
+  DP_CUDA(ctx, ctx->s_nvis.ensure(n * 4));
+  DP_CUDA(ctx, ctx->s_vis.ensure(n * vs * 4));
+  cudaStream_t st = ctx->stream;
+  DP_CUDA(ctx, cudaMemcpyAsync(ctx->s_pos.ptr, h->pos, n * 12, cudaMemcpyHostToDevice, st));
+  DP_CUDA(ctx, cudaMemcpyAsync(ctx->s_nrm.ptr, h->nrm, n * 12, cudaMemcpyHostToDevice, st));
+  DP_CUDA(ctx, cudaMemcpyAsync(ctx->s_ref.ptr, h->ref, n * 4, cudaMemcpyHostToDevice, st));
+  if (need_vis) {
+    DP_CUDA(ctx, cudaMemcpyAsync(ctx->s_nvis.ptr, h->nvis, n * 4, cudaMemcpyHostToDevice, st));
+    DP_CUDA(ctx, cudaMemcpyAsync(ctx->s_vis.ptr, h->vis, n * vs * 4, cudaMemcpyHostToDevice, st));
+  }
+  d->n = h->n;
+  d->vstride = h->vstride;
+  d->pos = ctx->s_pos.as<float>();
+  d->nrm = ctx->s_nrm.as<float>();
+  d->ref = ctx->s_ref.as<int32_t>();
+  d->nvis = ctx->s_nvis.as<int32_t>();
+  d->vis = ctx->s_vis.as<int32_t>();
+  d->rgb = nullptr;
+  return DP_OK;
+}
+
+extern "C" int dp_score(dp_context *ctx, const dp_patch_soa *h, int cell_size, float *ncc,
+                        uint8_t *tex, uint8_t *valid) {
+  if (!ctx) return DP_ERR_INVALID_ARG;
+  if (!ncc) return dp_fail(ctx, DP_ERR_INVALID_ARG, "ncc is null");
+  dp_patch_dev d;
+  int rc = upload_patches(ctx, h, &d, true);
+  if (rc != DP_OK) return rc;
+  if (h->n == 0) return DP_OK;
+  const size_t nv = (size_t)h->n * h->vstride;
+  const size_t tb = (size_t)cell_size * cell_size * 3;
+  DP_CUDA(ctx, ctx->s_ncc.ensure(nv * 4));
+  if (tex) DP_CUDA(ctx, ctx->s_tex.ensure(nv * tb));
+  if (valid) DP_CUDA(ctx, ctx->s_valid.ensure(nv));
+  rc = dp_score_dev(ctx, &d, cell_size, ctx->s_ncc.as<float>(), tex ? ctx->s_tex.as<uint8_t>() : nullptr,
+                    valid ? ctx->s_valid.as<uint8_t>() : nullptr, ctx->stream);
+  if (rc != DP_OK) return rc;
+  cudaStream_t st = ctx->stream;
+  DP_CUDA(ctx, cudaMemcpyAsync(ncc, ctx->s_ncc.ptr, nv * 4, cudaMemcpyDeviceToHost, st));
+  if (tex) DP_CUDA(ctx, cudaMemcpyAsync(tex, ctx->s_tex.ptr, nv * tb, cudaMemcpyDeviceToHost, st));
+  if (valid) DP_CUDA(ctx, cudaMemcpyAsync(valid, ctx->s_valid.ptr, nv, cudaMemcpyDeviceToHost, st));
+  DP_CUDA(ctx, cudaStreamSynchronize(st));
+  return DP_OK;
+}
+
+extern "C" int dp_filter(dp_context *ctx, dp_patch_soa *h, int cell_size, uint8_t *keep) {
+  if (!ctx) return DP_ERR_INVALID_ARG;
+  if (!keep) return dp_fail(ctx, DP_ERR_INVALID_ARG, "keep is null");
+  dp_patch_dev d;
+  int rc = upload_patches(ctx, h, &d, true);
+  if (rc != DP_OK) return rc;
+  if (h->n == 0) return DP_OK;
+  const size_t n = (size_t)h->n, vs = (size_t)h->vstride;
+  DP_CUDA(ctx, ctx->s_keep.ensure(n));
+  rc = dp_filter_dev(ctx, &d, cell_size, ctx->s_keep.as<uint8_t>(), ctx->stream);
+  if (rc != DP_OK) return rc;
+  cudaStream_t st = ctx->stream;
+  DP_CUDA(ctx, cudaMemcpyAsync(keep, ctx->s_keep.ptr, n, cudaMemcpyDeviceToHost, st));
+  DP_CUDA(ctx, cudaMemcpyAsync(h->nvis, d.nvis, n * 4, cudaMemcpyDeviceToHost, st));
+  DP_CUDA(ctx, cudaMemcpyAsync(h->vis, d.vis, n * vs * 4, cudaMemcpyDeviceToHost, st));
+  DP_CUDA(ctx, cudaStreamSynchronize(st));
+  return DP_OK;
+}
+
+extern "C" int dp_refine(dp_context *ctx, dp_patch_soa *h, int cell_size, const uint8_t *mask,
+                         int32_t *evals, double *xbest) {
+  if (!ctx) return DP_ERR_INVALID_ARG;
+  dp_patch_dev d;
+  int rc = upload_patches(ctx, h, &d, true);
+  if (rc != DP_OK) return rc;
+  if (h->n == 0) return DP_OK;
+  const size_t n = (size_t)h->n;
+  if (evals) DP_CUDA(ctx, ctx->s_evals.ensure(n * 4));
+  if (xbest) DP_CUDA(ctx, ctx->s_xbest.ensure(n * 24));
+  if (mask) {
+    DP_CUDA(ctx, ctx->s_keep.ensure(n));
+    DP_CUDA(ctx, cudaMemcpyAsync(ctx->s_keep.ptr, mask, n, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  rc = dp_refine_dev(ctx, &d, cell_size, mask ? ctx->s_keep.as<uint8_t>() : nullptr,
+                     evals ? ctx->s_evals.as<int32_t>() : nullptr,
+                     xbest ? ctx->s_xbest.as<double>() : nullptr, ctx->stream);
+  if (rc != DP_OK) return rc;
+  cudaStream_t st = ctx->stream;
+  DP_CUDA(ctx, cudaMemcpyAsync(h->pos, d.pos, n * 12, cudaMemcpyDeviceToHost, st));
+  DP_CUDA(ctx, cudaMemcpyAsync(h->nrm, d.nrm, n * 12, cudaMemcpyDeviceToHost, st));
+  if (evals) DP_CUDA(ctx, cudaMemcpyAsync(evals, ctx->s_evals.ptr, n * 4, cudaMemcpyDeviceToHost, st));
+  if (xbest) DP_CUDA(ctx, cudaMemcpyAsync(xbest, ctx->s_xbest.ptr, n * 24, cudaMemcpyDeviceToHost, st));
+  DP_CUDA(ctx, cudaStreamSynchronize(st));
+  return DP_OK;
+}
+
+extern "C" int dp_visibility(dp_context *ctx, dp_patch_soa *h, int32_t *ncand, int32_t *cand) {
+  if (!ctx) return DP_ERR_INVALID_ARG;
+  dp_patch_dev d;
+  int rc = upload_patches(ctx, h, &d, false);
+  if (rc != DP_OK) return rc;
+  if (h->n == 0) return DP_OK;
+  const size_t n = (size_t)h->n, vs = (size_t)h->vstride;
+  if (ncand) DP_CUDA(ctx, ctx->s_ncand.ensure(n * 4));
+  if (cand) DP_CUDA(ctx, ctx->s_cand.ensure(n * vs * 4));
+  rc = dp_visibility_dev(ctx, &d, ncand ? ctx->s_ncand.as<int32_t>() : nullptr,
+                         cand ? ctx->s_cand.as<int32_t>() : nullptr, ctx->stream);
+  if (rc != DP_OK) return rc;
+  cudaStream_t st = ctx->stream;
+  DP_CUDA(ctx, cudaMemcpyAsync(h->nvis, d.nvis, n * 4, cudaMemcpyDeviceToHost, st));
+  DP_CUDA(ctx, cudaMemcpyAsync(h->vis, d.vis, n * vs * 4, cudaMemcpyDeviceToHost, st));
+  if (ncand) DP_CUDA(ctx, cudaMemcpyAsync(ncand, ctx->s_ncand.ptr, n * 4, cudaMemcpyDeviceToHost, st));
+  if (cand) DP_CUDA(ctx, cudaMemcpyAsync(cand, ctx->s_cand.ptr, n * vs * 4, cudaMemcpyDeviceToHost, st));
+  DP_CUDA(ctx, cudaStreamSynchronize(st));
+  return DP_OK;
+}
+
+extern "C" int dp_color(dp_context *ctx, dp_patch_soa *h) {
+  if (!ctx || !h) return DP_ERR_INVALID_ARG;
+  if (h->n < 0 || (h->n > 0 && (!h->pos || !h->rgb)))
+    return dp_fail(ctx, DP_ERR_INVALID_ARG, "dp_color arguments");
+  if (h->n == 0) return DP_OK;
+  cudaSetDevice(ctx->device);
+  const size_t n = (size_t)h->n;
+  DP_CUDA(ctx, ctx->s_pos.ensure(n * 12));
+  DP_CUDA(ctx, ctx->s_rgb.ensure(n * 3));
+  cudaStream_t st = ctx->stream;
+  DP_CUDA(ctx, cudaMemcpyAsync(ctx->s_pos.ptr, h->pos, n * 12, cudaMemcpyHostToDevice, st));
+  dp_patch_dev d;
+  memset(&d, 0, sizeof(d));
+  d.n = h->n;
+  d.vstride = 1;
+  d.pos = ctx->s_pos.as<float>();
+  d.rgb = ctx->s_rgb.as<uint8_t>();
+  int rc = dp_color_dev(ctx, &d, st);
+  if (rc != DP_OK) return rc;
+  DP_CUDA(ctx, cudaMemcpyAsync(h->rgb, d.rgb, n * 3, cudaMemcpyDeviceToHost, st));
+  DP_CUDA(ctx, cudaStreamSynchronize(st));
+  return DP_OK;
+}
+
+#include "dp_expand.cuh"
+#include "dp_pyramid.cuh"

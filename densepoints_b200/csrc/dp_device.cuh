@@ -1,0 +1,311 @@
+// dp_device.cuh -- device-side building blocks of the PMVS photometric path (sm_100a).
+//
+// One warp owns one patch.  The warp walks the patch's visible views in order; for
+// every view it (1) projects the four patch corners (one corner per lane quad),
+// derives the ROI and the patch->ROI homography in closed form, (2) stages the ROI
+// pixels (packed BGRx) into a shared-memory tile with row-coalesced loads, (3) warps
+// the s x s texel grid through the homography with OpenCV's exact fixed-point
+// bilinear arithmetic (1/32 px coordinates, 15-bit weights, u8 rounding, 15-bit gray),
+// one texel per lane per pass, and (4) scores zero-mean NCC against the anchor (first
+// visible) texture, which stays in registers, with warp-shuffle reductions.
+//
+// Reference semantics implemented here (paths under the reference root):
+//   View::ProjectPoint / IsPointInside            modules/core/types.cpp:70-84
+//   Patch::GetProjectedXYAxisAndScale             methods/pmvs/patch.cpp:86-104
+//   Patch::ComputePatchToViewHomography           methods/pmvs/patch.cpp:111-164
+//   Optimization::GetProjectedTextures            methods/pmvs/optimization.cpp:14-56
+//   cv::warpPerspective(INTER_LINEAR, BORDER_REPLICATE) + cv::cvtColor(BGR2GRAY)
+//   NCCScore                                      modules/core/error_measurements.cpp:36-60
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct DpViewDev {
+  double P[12];      // View::GetProjectionMatrix(), row-major 3x4
+  double xa[3];      // View::GetXAxis().normalized()
+  double center[3];  // View::GetCameraCenter()
+  const uint32_t *img;  // packed BGRx, pitch_px pixels per row
+  int width, height, pitch_px;
+  int gw, gh;              // PatchGrid dims: width / grid_scale, height / grid_scale
+  long long grid_off;      // offset of this view's grid in the occupancy array
+};
+
+#define DP_FULL 0xffffffffu
+
+// fp64 operations that must not be contracted into FMAs: the set-up chain
+// (axes -> corners -> projection -> fp32 points -> ROI) mirrors the reference's
+// unfused evaluation order so the fp32-rounded quad and the integer ROI agree.
+__device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double xadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double xsub(double a, double b) { return __dsub_rn(a, b); }
+
+__device__ __forceinline__ void dp_project(const double *__restrict__ P, double X0, double X1,
+                                           double X2, double &u, double &v) {
+  double x = xadd(xadd(xadd(xmul(P[0], X0), xmul(P[1], X1)), xmul(P[2], X2)), P[3]);
+  double y = xadd(xadd(xadd(xmul(P[4], X0), xmul(P[5], X1)), xmul(P[6], X2)), P[7]);
+  double w = xadd(xadd(xadd(xmul(P[8], X0), xmul(P[9], X1)), xmul(P[10], X2)), P[11]);
+  u = x / w;
+  v = y / w;
+}
+
+// 1/W to ~1 ulp without the IEEE-division slow path: hardware seed (20 bits) plus two
+// Newton steps.  The result only feeds a coordinate that is then quantised to 1/32 px.
+__device__ __forceinline__ double dp_rcp(double w) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(w));
+  double e = fma(-w, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-w, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(DP_FULL, v, o);
+  return v;
+}
+
+// Per-patch frame: scaled patch axes in world units (optimization.cpp:19-30).
+struct DpFrame {
+  double p[3];   // patch centre
+  double ax[3];  // scale * x_axis
+  double ay[3];  // scale * y_axis (y = n x x, not normalised, patch.cpp:96)
+  bool ok;       // false when dx == 0 (LOG(FATAL) in the reference, optimization.cpp:27)
+};
+
+__device__ __forceinline__ void dp_make_frame(const DpViewDev *__restrict__ ref, int s,
+                                              const double n[3], const double p[3], DpFrame &f) {
+  const double xa0 = ref->xa[0], xa1 = ref->xa[1], xa2 = ref->xa[2];
+  // y_axis = normal.cross(x_axis)
+  double ya0 = xsub(xmul(n[1], xa2), xmul(n[2], xa1));
+  double ya1 = xsub(xmul(n[2], xa0), xmul(n[0], xa2));
+  double ya2 = xsub(xmul(n[0], xa1), xmul(n[1], xa0));
+  double cu, cv, qu, qv;
+  dp_project(ref->P, p[0], p[1], p[2], cu, cv);
+  dp_project(ref->P, xadd(p[0], xa0), xadd(p[1], xa1), xadd(p[2], xa2), qu, qv);
+  double du = xsub(qu, cu), dv = xsub(qv, cv);
+  double dx = sqrt(xadd(xmul(du, du), xmul(dv, dv)));
+  f.ok = (dx != 0.0) && isfinite(dx);
+  double scale = (double)(s / 2) / dx;  // integer cell_size / 2 (optimization.cpp:30)
+  f.p[0] = p[0]; f.p[1] = p[1]; f.p[2] = p[2];
+  f.ax[0] = xmul(scale, xa0); f.ax[1] = xmul(scale, xa1); f.ax[2] = xmul(scale, xa2);
+  f.ay[0] = xmul(scale, ya0); f.ay[1] = xmul(scale, ya1); f.ay[2] = xmul(scale, ya2);
+}
+
+// Per-lane texel grid: texel i = lane + 32*j of the s x s destination, row-major.
+// Up to 8 passes (s <= 16) the coordinates live in registers; above that they are
+// recomputed per texel to keep the register count bounded.
+template <int NPASS, bool PRE = (NPASS <= 8)>
+struct DpTexels {
+  double x[NPASS], y[NPASS];
+  __device__ __forceinline__ void init(int s, int lane) {
+#pragma unroll
+    for (int j = 0; j < NPASS; ++j) {
+      int i = lane + 32 * j;
+      int yy = i / s;
+      x[j] = (double)(i - yy * s);
+      y[j] = (double)yy;
+    }
+  }
+  __device__ __forceinline__ void get(int j, int, double &xo, double &yo) const {
+    xo = x[j];
+    yo = y[j];
+  }
+};
+template <int NPASS>
+struct DpTexels<NPASS, false> {
+  int s_;
+  float inv_s_;
+  __device__ __forceinline__ void init(int s, int) {
+    s_ = s;
+    inv_s_ = 1.0f / (float)s;
+  }
+  __device__ __forceinline__ void get(int, int i, double &xo, double &yo) const {
+    int yy = (int)(((float)i + 0.5f) * inv_s_);
+    xo = (double)(i - yy * s_);
+    yo = (double)yy;
+  }
+};
+
+// The texture of one view: gray value of every texel owned by this lane
+// (g[j], 0..255), optionally the BGR texels themselves.  Returns false where the
+// reference pushes an empty cv::Mat (corner outside, ROI <= 0, degenerate quad).
+// `tile` is this warp's shared-memory staging buffer of tile_cap pixels.
+template <int NPASS, bool WRITE_TEX>
+__device__ __forceinline__ bool dp_view_texture(const DpViewDev *__restrict__ V, int s, int npx,
+                                                const DpFrame &f, const DpTexels<NPASS> &tx,
+                                                uint32_t *tile, int tile_cap, int lane,
+                                                int (&g)[NPASS], uint8_t *__restrict__ tex_out) {
+  // ---- corners (patch.cpp:119-135): lane&3 = corner (-,-) (+,-) (+,+) (-,+) ------------
+  const int c = lane & 3;
+  const double sgx = (c == 1 || c == 2) ? 1.0 : -1.0;
+  const double sgy = (c >= 2) ? 1.0 : -1.0;
+  double X0 = xadd(xadd(f.p[0], sgx * f.ax[0]), sgy * f.ay[0]);
+  double X1 = xadd(xadd(f.p[1], sgx * f.ax[1]), sgy * f.ay[1]);
+  double X2 = xadd(xadd(f.p[2], sgx * f.ax[2]), sgy * f.ay[2]);
+  double u, v;
+  dp_project(V->P, X0, X1, X2, u, v);
+  const int W = V->width, H = V->height;
+  bool in = (u > 0) && (u < (double)W) && (v > 0) && (v < (double)H);  // IsPointInside
+  if (!__all_sync(DP_FULL, in)) return false;
+  // ---- ROI: tl = min ceil, br = max floor (patch.cpp:126-147) ---------------------------
+  int tlx = (int)ceil(u), tly = (int)ceil(v), brx = (int)floor(u), bry = (int)floor(v);
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {
+    tlx = min(tlx, __shfl_xor_sync(DP_FULL, tlx, o));
+    tly = min(tly, __shfl_xor_sync(DP_FULL, tly, o));
+    brx = max(brx, __shfl_xor_sync(DP_FULL, brx, o));
+    bry = max(bry, __shfl_xor_sync(DP_FULL, bry, o));
+  }
+  tlx = min(tlx, W); tly = min(tly, H); brx = max(brx, 0); bry = max(bry, 0);
+  const int rw = brx - tlx, rh = bry - tly;
+  if (rw <= 0 || rh <= 0) return false;  // optimization.cpp:45
+  // cv::Point2f, then `-= roi.x` in fp32 (patch.cpp:134, 148-151)
+  float fx = __fsub_rn((float)u, (float)tlx);
+  float fy = __fsub_rn((float)v, (float)tly);
+  double qx0 = (double)__shfl_sync(DP_FULL, fx, 0), qy0 = (double)__shfl_sync(DP_FULL, fy, 0);
+  double qx1 = (double)__shfl_sync(DP_FULL, fx, 1), qy1 = (double)__shfl_sync(DP_FULL, fy, 1);
+  double qx2 = (double)__shfl_sync(DP_FULL, fx, 2), qy2 = (double)__shfl_sync(DP_FULL, fy, 2);
+  double qx3 = (double)__shfl_sync(DP_FULL, fx, 3), qy3 = (double)__shfl_sync(DP_FULL, fy, 3);
+  // ---- homography (patch.cpp:153-161 + cv::warpPerspective's inversion) -----------------
+  // cv::findHomography on 4 points is the exact projective map quad -> [0,s]^2 and
+  // warpPerspective uses its inverse; that inverse (cell -> quad) has the closed form
+  // below (unit square -> quad), so no 9x9 eigen-solve and no 3x3 inversion are needed.
+  double sxq = qx0 - qx1 + qx2 - qx3, syq = qy0 - qy1 + qy2 - qy3;
+  double dx1 = qx1 - qx2, dx2 = qx3 - qx2, dy1 = qy1 - qy2, dy2 = qy3 - qy2;
+  double den = dx1 * dy2 - dx2 * dy1;
+  if (!(den != 0.0)) return false;
+  double rden = 1.0 / den;
+  double gq = (sxq * dy2 - dx2 * syq) * rden;
+  double hq = (dx1 * syq - sxq * dy1) * rden;
+  const double inv_s = 1.0 / (double)s;
+  // source = (M0 x + M1 y + M2, M3 x + M4 y + M5) / (M6 x + M7 y + 1), pre-scaled by the
+  // 1/32-px factor INTER_TAB_SIZE
+  const double M0 = 32.0 * (qx1 - qx0 + gq * qx1) * inv_s, M1 = 32.0 * (qx3 - qx0 + hq * qx3) * inv_s;
+  const double M2 = 32.0 * qx0;
+  const double M3 = 32.0 * (qy1 - qy0 + gq * qy1) * inv_s, M4 = 32.0 * (qy3 - qy0 + hq * qy3) * inv_s;
+  const double M5 = 32.0 * qy0;
+  const double M6 = gq * inv_s, M7 = hq * inv_s;
+  if (!(isfinite(M0) && isfinite(M1) && isfinite(M3) && isfinite(M4) && isfinite(M6) &&
+        isfinite(M7)))
+    return false;
+  // ---- stage the ROI into shared memory (row-coalesced) ---------------------------------
+  const uint32_t *__restrict__ src = V->img + (size_t)tly * V->pitch_px + tlx;
+  const int pitch = V->pitch_px;
+  const int area = rw * rh;
+  const bool staged = area <= tile_cap;
+  if (staged) {
+    __syncwarp();
+    const float inv_w = 1.0f / (float)rw;
+    for (int t = lane; t < area; t += 32) {
+      int r = (int)(((float)t + 0.5f) * inv_w);
+      int cidx = t - r * rw;
+      tile[t] = __ldg(src + (size_t)r * pitch + cidx);
+    }
+    __syncwarp();
+  }
+  // ---- warp the texel grid --------------------------------------------------------------
+#pragma unroll
+  for (int j = 0; j < NPASS; ++j) {
+    const int i = lane + 32 * j;
+    g[j] = 0;
+    if (i < npx) {
+      double x, y;
+      tx.get(j, i, x, y);
+      double Wd = fma(M6, x, fma(M7, y, 1.0));
+      double r = dp_rcp(Wd);
+      r = (Wd != 0.0) ? r : 0.0;  // W ? INTER_TAB_SIZE / W : 0
+      double fX = fma(M0, x, fma(M1, y, M2)) * r;
+      double fY = fma(M3, x, fma(M4, y, M5)) * r;
+      int Xi = __double2int_rn(fX);  // saturate_cast<int>(cvRound), half to even
+      int Yi = __double2int_rn(fY);
+      int sx = Xi >> 5, axw = Xi & 31;  // INTER_BITS = 5
+      int sy = Yi >> 5, ayw = Yi & 31;
+      int x0 = min(max(sx, 0), rw - 1), x1 = min(max(sx + 1, 0), rw - 1);  // BORDER_REPLICATE
+      int y0 = min(max(sy, 0), rh - 1), y1 = min(max(sy + 1, 0), rh - 1);  // at the ROI edge
+      uint32_t p00, p01, p10, p11;
+      if (staged) {
+        p00 = tile[y0 * rw + x0]; p01 = tile[y0 * rw + x1];
+        p10 = tile[y1 * rw + x0]; p11 = tile[y1 * rw + x1];
+      } else {
+        const uint32_t *r0 = src + (size_t)y0 * pitch, *r1 = src + (size_t)y1 * pitch;
+        p00 = __ldg(r0 + x0); p01 = __ldg(r0 + x1);
+        p10 = __ldg(r1 + x0); p11 = __ldg(r1 + x1);
+      }
+      // separable form of the 15-bit weights (32-ax)(32-ay)*32 ...: exact in integers,
+      // (sum*32 + 2^14) >> 15 == (sum + 2^9) >> 10.
+      const uint32_t wx1 = (uint32_t)axw, wx0 = 32u - wx1, wy1 = (uint32_t)ayw, wy0 = 32u - wy1;
+      uint32_t br0 = (p00 & 0x00ff00ffu) * wx0 + (p01 & 0x00ff00ffu) * wx1;  // B | R<<16
+      uint32_t br1 = (p10 & 0x00ff00ffu) * wx0 + (p11 & 0x00ff00ffu) * wx1;
+      uint32_t g0 = ((p00 >> 8) & 0xffu) * wx0 + ((p01 >> 8) & 0xffu) * wx1;
+      uint32_t g1 = ((p10 >> 8) & 0xffu) * wx0 + ((p11 >> 8) & 0xffu) * wx1;
+      uint32_t B = ((br0 & 0xffffu) * wy0 + (br1 & 0xffffu) * wy1 + 512u) >> 10;
+      uint32_t R = ((br0 >> 16) * wy0 + (br1 >> 16) * wy1 + 512u) >> 10;
+      uint32_t G = (g0 * wy0 + g1 * wy1 + 512u) >> 10;
+      // cv::cvtColor(BGR2GRAY), 8U: 15-bit fixed point
+      g[j] = (int)((3735u * B + 19235u * G + 9798u * R + (1u << 14)) >> 15);
+      if (WRITE_TEX) {
+        tex_out[3 * i + 0] = (uint8_t)B;
+        tex_out[3 * i + 1] = (uint8_t)G;
+        tex_out[3 * i + 2] = (uint8_t)R;
+      }
+    }
+  }
+  return true;
+}
+
+// Zero-mean NCC state of the anchor texture (NCCScore on textures[0]).
+template <int NPASS>
+struct DpAnchor {
+  float d[NPASS];  // fl32(a_i - fl32(mean_a)), `Mat - scalar` on CV_32F
+  double std;      // population sigma (cv::meanStdDev)
+  bool valid;
+};
+
+// cv::meanStdDev on the gray texels held by the warp: integer sums are exact.
+template <int NPASS>
+__device__ __forceinline__ void dp_mean_std(const int (&g)[NPASS], int npx, double &mean,
+                                            double &stdv) {
+  unsigned s1 = 0, s2 = 0;
+#pragma unroll
+  for (int j = 0; j < NPASS; ++j) {
+    s1 += (unsigned)g[j];
+    s2 += (unsigned)(g[j] * g[j]);
+  }
+  s1 = __reduce_add_sync(DP_FULL, s1);
+  s2 = __reduce_add_sync(DP_FULL, s2);
+  const double scale = 1.0 / (double)npx;
+  mean = xmul((double)s1, scale);
+  double var = xsub(xmul((double)s2, scale), xmul(mean, mean));
+  stdv = sqrt(var > 0.0 ? var : 0.0);
+}
+
+template <int NPASS>
+__device__ __forceinline__ void dp_set_anchor(const int (&g)[NPASS], int npx, int lane,
+                                              DpAnchor<NPASS> &a) {
+  double mean;
+  dp_mean_std<NPASS>(g, npx, mean, a.std);
+  const float mf = (float)mean;
+#pragma unroll
+  for (int j = 0; j < NPASS; ++j) a.d[j] = (lane + 32 * j < npx) ? __fsub_rn((float)g[j], mf) : 0.f;
+}
+
+// NCCScore(anchor, this view) (error_measurements.cpp:47-59)
+template <int NPASS>
+__device__ __forceinline__ double dp_ncc(const DpAnchor<NPASS> &a, const int (&g)[NPASS], int npx,
+                                         int lane) {
+  double mean, stdv;
+  dp_mean_std<NPASS>(g, npx, mean, stdv);
+  const float mf = (float)mean;
+  double num = 0.0;
+#pragma unroll
+  for (int j = 0; j < NPASS; ++j) {
+    float db = (lane + 32 * j < npx) ? __fsub_rn((float)g[j], mf) : 0.f;
+    num = xadd(num, xmul((double)a.d[j], (double)db));
+  }
+  num = warp_sum_f64(num);
+  double den = xmul(a.std, stdv);
+  den = den > 1e-1 ? den : 1e-1;
+  return (num / den) / (double)npx;
+}

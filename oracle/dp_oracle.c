@@ -329,10 +329,8 @@ static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v
  * OpenCV's WarpPerspectiveInvoker + remap fixed-point bilinear (SURVEY a4,
  * Appendix A): M = H^-1 in fp64; source coordinates quantised to 1/32 px with
  * round-half-even; taps clamped to the ROI; 15-bit integer weights. */
-void orc_warp_perspective(const uint8_t *src, size_t stride, int w, int h, const double H[9],
-                          int s, uint8_t *dst) {
-  double M[9];
-  invert3(H, M);
+static void warp_with_M(const uint8_t *src, size_t stride, int w, int h, const double M[9], int s,
+                        uint8_t *dst) {
   for (int y = 0; y < s; ++y) {
     double X0 = M[1] * y + M[2];
     double Y0 = M[4] * y + M[5];
@@ -363,6 +361,46 @@ void orc_warp_perspective(const uint8_t *src, size_t stride, int w, int h, const
     }
   }
 }
+
+void orc_warp_perspective(const uint8_t *src, size_t stride, int w, int h, const double H[9],
+                          int s, uint8_t *dst) {
+  double M[9];
+  invert3(H, M);
+  warp_with_M(src, stride, w, h, M, s, dst);
+}
+
+/* The exact projective map cell [0,s]^2 -> quad, i.e. what
+ * invert(findHomography(quad -> cell)) is mathematically (closed form of the
+ * unit-square-to-quadrilateral mapping).  Used in homography mode 1, see
+ * orc_set_homography_mode. Returns 0 for a degenerate quad. */
+int orc_cell_to_quad(const float q[8], int s, double M[9]) {
+  double qx0 = q[0], qy0 = q[1], qx1 = q[2], qy1 = q[3], qx2 = q[4], qy2 = q[5], qx3 = q[6],
+         qy3 = q[7];
+  double sx = qx0 - qx1 + qx2 - qx3, sy = qy0 - qy1 + qy2 - qy3;
+  double dx1 = qx1 - qx2, dx2 = qx3 - qx2, dy1 = qy1 - qy2, dy2 = qy3 - qy2;
+  double den = dx1 * dy2 - dx2 * dy1;
+  if (!(den != 0.0)) return 0;
+  double rden = 1.0 / den;
+  double g = (sx * dy2 - dx2 * sy) * rden;
+  double h = (dx1 * sy - sx * dy1) * rden;
+  double inv_s = 1.0 / (double)s;
+  M[0] = (qx1 - qx0 + g * qx1) * inv_s;
+  M[1] = (qx3 - qx0 + h * qx3) * inv_s;
+  M[2] = qx0;
+  M[3] = (qy1 - qy0 + g * qy1) * inv_s;
+  M[4] = (qy3 - qy0 + h * qy3) * inv_s;
+  M[5] = qy0;
+  M[6] = g * inv_s;
+  M[7] = h * inv_s;
+  M[8] = 1.0;
+  for (int i = 0; i < 8; ++i)
+    if (!isfinite(M[i])) return 0;
+  return 1;
+}
+
+static int g_homography_mode = 0;
+void orc_set_homography_mode(int mode) { g_homography_mode = mode; }
+int orc_get_homography_mode(void) { return g_homography_mode; }
 
 /* cv::DownhillSolver::minimize (OpenCV >= 3.0 core/downhill_simplex.cpp), called
  * at optimization_opencv.cpp:63.  PARITY UNPINNED against upstream: the solver's
@@ -508,12 +546,12 @@ void orc_axes_scale(const orc_view *ref, const double nrm[3], const double pos[3
   *dx = sqrt(du * du + dv * dv);
 }
 
-/* Patch::ComputePatchToViewHomography (patch.cpp:111-164) */
-int orc_patch_homography(const orc_view *v, int cell_size, const double pos[3], const double ax[3],
-                         const double ay[3], double H[9], int roi[4]) {
+/* Patch::ComputePatchToViewHomography (patch.cpp:111-151): projected quad relative to
+ * the ROI (fp32 cv::Point2f) and the ROI itself. */
+int orc_patch_quad(const orc_view *v, const double pos[3], const double ax[3], const double ay[3],
+                   float pts[8], int roi[4]) {
   static const double sgn[4][2] = {{-1, -1}, {+1, -1}, {+1, +1}, {-1, +1}}; /* :119-123 */
   int tlx = v->width, tly = v->height, brx = 0, bry = 0;                     /* :126 */
-  float pts[8];
   for (int i = 0; i < 4; ++i) {
     double X[3];
     for (int j = 0; j < 3; ++j) X[j] = pos[j] + sgn[i][0] * ax[j] + sgn[i][1] * ay[j];
@@ -537,6 +575,14 @@ int orc_patch_homography(const orc_view *v, int cell_size, const double pos[3], 
     pts[2 * i] -= (float)roi[0];
     pts[2 * i + 1] -= (float)roi[1];
   }
+  return 1;
+}
+
+/* Patch::ComputePatchToViewHomography (patch.cpp:111-164) */
+int orc_patch_homography(const orc_view *v, int cell_size, const double pos[3], const double ax[3],
+                         const double ay[3], double H[9], int roi[4]) {
+  float pts[8];
+  if (!orc_patch_quad(v, pos, ax, ay, pts, roi)) return 0;
   float cs = (float)cell_size;
   float cell[8] = {0, 0, cs, 0, cs, cs, 0, cs};
   if (!orc_find_homography4(pts, cell, H)) return -1; /* empty H: OpenCV would throw */
@@ -562,15 +608,26 @@ void orc_projected_textures(const orc_view *views, int ref, const int *vis, int 
   }
   for (int k = 0; k < nvis; ++k) {
     const orc_view *v = &views[vis[k]];
-    double H[9];
+    double H[9], M[9];
     int roi[4];
-    int ok = orc_patch_homography(v, cell_size, pos, ax, ay, H, roi);
+    int ok;
+    if (g_homography_mode == 0) {
+      ok = orc_patch_homography(v, cell_size, pos, ax, ay, H, roi);
+    } else {
+      float pts[8];
+      ok = orc_patch_quad(v, pos, ax, ay, pts, roi);
+      if (ok > 0 && roi[2] > 0 && roi[3] > 0) ok = orc_cell_to_quad(pts, s, M) ? 1 : -1;
+    }
     if (ok <= 0 || roi[2] <= 0 || roi[3] <= 0) { /* :45-48 */
       valid[k] = 0;
       continue;
     }
     const uint8_t *src = v->bgr + (size_t)roi[1] * v->stride + 3 * (size_t)roi[0];
-    orc_warp_perspective(src, v->stride, roi[2], roi[3], H, s, tex + (size_t)k * s * s * 3);
+    uint8_t *dst = tex + (size_t)k * s * s * 3;
+    if (g_homography_mode == 0)
+      orc_warp_perspective(src, v->stride, roi[2], roi[3], H, s, dst);
+    else
+      warp_with_M(src, v->stride, roi[2], roi[3], M, s, dst);
     valid[k] = 1;
   }
 }

@@ -82,6 +82,21 @@ int orc_find_homography4(const float src[8], const float dst[8], double H[9]);
 /* cv::warpPerspective(src(roi), H, (s,s), INTER_LINEAR, BORDER_REPLICATE), 8UC3. */
 void orc_warp_perspective(const uint8_t *src, size_t stride, int w, int h, const double H[9],
                           int s, uint8_t *dst);
+/* Homography mode of GetProjectedTextures:
+ *   0 (default) = the OpenCV procedure: findHomography's normalised DLT + Jacobi
+ *       eigen-solve, then warpPerspective's 3x3 inversion.  Pinned against cv2.
+ *   1 = the exact projective map cell -> quad in closed form (orc_cell_to_quad).
+ * The two differ by ~1e-14 px in the source coordinates, which changes a texel only at
+ * an exact tie (a coordinate of exactly k + 1/2 in 1/32-px units, reachable at texel
+ * (0,0) because the quad corner is an fp32 number): there OpenCV's own result is decided
+ * by the sign of its eigen-solver's rounding noise, i.e. it is not a function of the
+ * inputs.  Mode 1 defines the tie by the exact value and is what the CUDA path is
+ * checked against. */
+void orc_set_homography_mode(int mode);
+int orc_get_homography_mode(void);
+int orc_cell_to_quad(const float quad[8], int s, double M[9]);
+int orc_patch_quad(const orc_view *v, const double pos[3], const double ax[3], const double ay[3],
+                   float pts[8], int roi[4]);
 /* cv::cvtColor(BGR2GRAY) for one pixel (OpenCV 4.x 15-bit constants). */
 int orc_gray(int b, int g, int r);
 /* cv::DownhillSolver::minimize restated (ndim <= 8). Returns f(best); x <- best. */

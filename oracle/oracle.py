@@ -314,5 +314,15 @@ class Organizer:
         return lib().orc_expand_patches_fifo(self.h, C.c_int(cell_size), C.c_longlong(max_pops))
 
 
+def set_homography_mode(mode: int):
+    """0 = OpenCV's DLT + eigen-solve + inversion (pinned against cv2); 1 = exact closed form
+    (deterministic at ties; what the CUDA path is checked against).  See dp_oracle.h."""
+    lib().orc_set_homography_mode(C.c_int(mode))
+
+
+def get_homography_mode() -> int:
+    return lib().orc_get_homography_mode()
+
+
 def num_threads():
     return lib().orc_num_threads()

@@ -1,0 +1,189 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle and
+the cv2-made golden vectors.  Bars: textures / visibility / filter / cells / colours
+bit-exact; NCC and refined depth <= 1e-4 abs; normals <= 0.05 deg."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi_mod():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from densepoints_b200 import build as b
+    b.build_cuda()
+    from densepoints_b200 import capi
+    return capi
+
+
+@pytest.fixture(scope="module")
+def exact_orc(orc):
+    orc.set_homography_mode(1)     # exact projective map: deterministic at ties (dp_oracle.h)
+    yield orc
+    orc.set_homography_mode(0)
+
+
+@pytest.fixture(scope="module")
+def c1(capi_mod, exact_orc):
+    """Config C1: 3 cameras, textured plane, 640x480."""
+    from densepoints_b200 import scenes
+    sc = scenes.make_plane_scene(seed=1, n_views=3, width=640, height=480)
+    seeds = scenes.make_seeds(sc, 2000, seed=1)
+    ctx = capi_mod.Context(0, capi_mod.default_params(minimum_visible_image=2))
+    ctx.set_views(sc.P, sc.images)
+    V = exact_orc.Views(sc.P, sc.images)
+    nvis, vis, _, _ = exact_orc.visibility_batch(V, seeds["pos"], seeds["nrm"], seeds["ref"])
+    yield dict(sc=sc, seeds=seeds, ctx=ctx, V=V, nvis=nvis, vis=vis)
+    ctx.close()
+
+
+def angle_deg(a, b):
+    a = a.astype(np.float64)
+    b = b.astype(np.float64)
+    c = (a * b).sum(1) / (np.linalg.norm(a, axis=1) * np.linalg.norm(b, axis=1))
+    return np.degrees(np.arccos(np.clip(c, -1, 1)))
+
+
+def test_view_decomposition(capi_mod, c1, exact_orc):
+    for i in range(c1["sc"].n_views):
+        xa, ce, w, h = c1["ctx"].get_view(i)
+        assert np.abs(xa - c1["V"].xaxis(i)).max() < 1e-12
+        assert np.abs(ce - c1["V"].center(i)).max() < 1e-9
+        assert (w, h) == (640, 480)
+
+
+def test_golden_textures_ncc_filter(capi_mod, golden_scoring):
+    """CUDA vs the cv2-made golden vectors (real OpenCV arithmetic)."""
+    g = golden_scoring
+    ctx = capi_mod.Context(0, capi_mod.default_params(minimum_visible_image=2))
+    ctx.set_views(g["P"], list(g["images"]), xaxes=g["xaxis"], centers=g["center"])
+    for s in (5, 7, 11, 16):
+        ncc, tex, valid = ctx.score(g["pos"], g["nrm"], g["ref"], g["nvis"], g["vis"], s,
+                                    want_tex=True)
+        assert np.array_equal(valid, g[f"valid{s}"])
+        diff = (tex != g[f"tex{s}"]).any(axis=-1)          # (n, V, s, s) texel mismatch
+        # OpenCV's own result is noise-dependent at an exact 1/64-px tie of texel (0,0)
+        # (dp_oracle.h "homography mode"); nothing else may differ.
+        assert diff[..., 1:, :].sum() == 0 and diff[..., 0, 1:].sum() == 0
+        assert diff.sum() <= 3
+        k = np.arange(g["vis"].shape[1])[None, :]
+        sm = (k >= 1) & (k < g["nvis"][:, None])
+        clean = ~diff.any(axis=(2, 3))
+        clean = clean & clean[:, :1]
+        assert np.abs(ncc[sm & clean] - g[f"ncc{s}"][sm & clean]).max() < 5e-6   # bar 1e-4
+        if diff.sum() == 0:
+            keep, fnvis, fvis = ctx.filter(g["pos"], g["nrm"], g["ref"], g["nvis"], g["vis"], s)
+            assert np.array_equal(keep, g[f"keep{s}"])
+            assert np.array_equal(fnvis, g[f"fnvis{s}"])
+            assert np.array_equal(fvis, g[f"fvis{s}"])
+    ctx.close()
+
+
+@pytest.mark.parametrize("s", [5, 7, 11, 16, 3, 20, 32])
+def test_score_vs_oracle(c1, exact_orc, s):
+    d = c1
+    sd = d["seeds"]
+    n = 2000 if s <= 16 else 300
+    sl = slice(0, n)
+    ncc, tex, valid = d["ctx"].score(sd["pos"][sl], sd["nrm"][sl], sd["ref"][sl], d["nvis"][sl],
+                                     d["vis"][sl], s, want_tex=True)
+    o_ncc, o_tex, o_valid = exact_orc.score_batch(d["V"], sd["pos"][sl], sd["nrm"][sl],
+                                                  sd["ref"][sl], d["nvis"][sl], d["vis"][sl], s,
+                                                  want_tex=True)
+    assert np.array_equal(valid, o_valid)
+    assert np.array_equal(tex, o_tex)                       # bit-exact u8 textures
+    assert np.abs(ncc - o_ncc).max() < 1e-6                 # bar 1e-4
+    # no-texture path must give the same scores
+    ncc2 = d["ctx"].score(sd["pos"][sl], sd["nrm"][sl], sd["ref"][sl], d["nvis"][sl],
+                          d["vis"][sl], s)
+    assert np.array_equal(ncc, ncc2)
+
+
+@pytest.mark.parametrize("s", [5, 7, 16])
+def test_filter_vs_oracle(c1, exact_orc, s):
+    d = c1
+    sd = d["seeds"]
+    keep, nvis, vis = d["ctx"].filter(sd["pos"], sd["nrm"], sd["ref"], d["nvis"], d["vis"], s)
+    o_keep, o_nvis, o_vis = exact_orc.filter_batch(d["V"], sd["pos"], sd["nrm"], sd["ref"],
+                                                   d["nvis"], d["vis"], s, 0.6, 2)
+    assert np.array_equal(keep, o_keep)
+    assert np.array_equal(nvis, o_nvis)
+    assert np.array_equal(vis, o_vis)
+    assert 0 < keep.sum() < len(keep)
+
+
+def test_visibility_and_color_vs_oracle(c1, exact_orc):
+    d = c1
+    sd = d["seeds"]
+    nvis, vis, ncand, cand = d["ctx"].visibility(sd["pos"], sd["nrm"], sd["ref"])
+    o = exact_orc.visibility_batch(d["V"], sd["pos"], sd["nrm"], sd["ref"])
+    for a, b in zip((nvis, vis, ncand, cand), o):
+        assert np.array_equal(a, b)
+    rgb = d["ctx"].color(sd["pos"])
+    assert np.array_equal(rgb, exact_orc.compute_color(d["V"], sd["pos"]))
+
+
+@pytest.mark.parametrize("s,n", [(5, 2000), (7, 600), (11, 300), (16, 200)])
+def test_refine_vs_oracle(c1, exact_orc, s, n):
+    d = c1
+    sd = d["seeds"]
+    sl = slice(0, n)
+    pos, nrm, evals, xb = d["ctx"].refine(sd["pos"][sl], sd["nrm"][sl], sd["ref"][sl],
+                                          d["nvis"][sl], d["vis"][sl], s)
+    o_pos, o_nrm, o_fc, o_xb = exact_orc.refine_batch(d["V"], sd["pos"][sl], sd["nrm"][sl],
+                                                      sd["ref"][sl], d["nvis"][sl], d["vis"][sl], s)
+    assert np.array_equal(evals, o_fc)                      # identical Nelder-Mead trajectory
+    assert np.abs(xb - o_xb).max() < 1e-12
+    C = d["sc"].centers[sd["ref"][sl]]
+    depth = np.linalg.norm(pos.astype(np.float64) - C, axis=1)
+    o_depth = np.linalg.norm(o_pos.astype(np.float64) - C, axis=1)
+    assert np.abs(depth - o_depth).max() <= 1e-4            # the stated bar
+    assert angle_deg(nrm, o_nrm).max() <= 0.05
+    assert np.array_equal(pos, o_pos) and np.array_equal(nrm, o_nrm)   # in fact bit-exact fp32
+    assert evals.min() >= 4 and evals.max() <= 503
+
+
+def test_refine_improves_photoconsistency(c1):
+    d = c1
+    sd = d["seeds"]
+    m = d["nvis"] >= 2
+    before = d["ctx"].score(sd["pos"], sd["nrm"], sd["ref"], d["nvis"], d["vis"], 5)[m, 1]
+    pos, nrm, evals, _ = d["ctx"].refine(sd["pos"], sd["nrm"], sd["ref"], d["nvis"], d["vis"], 5)
+    after = d["ctx"].score(pos, nrm, sd["ref"], d["nvis"], d["vis"], 5)[m, 1]
+    assert np.median(after) > np.median(before) + 0.1
+    # the plane is z = 0: refinement must pull the seeds towards it
+    assert np.abs(pos[m, 2]).mean() < np.abs(sd["pos"][m, 2]).mean()
+
+
+def test_edge_cases(capi_mod, c1):
+    ctx = c1["ctx"]
+    sd = c1["seeds"]
+    # empty batch
+    e3 = np.zeros((0, 3), np.float32)
+    assert ctx.score(e3, e3, np.zeros(0, np.int32), np.zeros(0, np.int32),
+                     np.zeros((0, 2), np.int32), 5).shape == (0, 2)
+    # patches with 0 / 1 visible views: no scores; filter drops them, refine still "succeeds"
+    pos, nrm, ref = sd["pos"][:4], sd["nrm"][:4], sd["ref"][:4]
+    nvis = np.array([0, 1, 0, 1], np.int32)
+    vis = np.full((4, 2), -1, np.int32)
+    vis[1, 0] = (ref[1] + 1) % 3
+    vis[3, 0] = (ref[3] + 2) % 3
+    keep, nv2, vis2 = ctx.filter(pos, nrm, ref, nvis, vis, 5)
+    assert keep.sum() == 0 and np.array_equal(nv2, nvis) and np.array_equal(vis2, vis)
+    p2, n2, ev, xb = ctx.refine(pos, nrm, ref, nvis, vis, 5)
+    assert (ev == 4).all()                                 # f == 2 everywhere: stops at once
+    assert np.allclose(xb, [0.0, 0.0, 0.1])                # best = last vertex of the tie
+    # a patch far outside every image: all textures empty -> NCC = -1
+    far = sd["pos"][:1].copy()
+    far[0, 0] += 500.0
+    ncc, tex, valid = ctx.score(far, sd["nrm"][:1], sd["ref"][:1], np.array([2], np.int32),
+                                np.array([[(sd["ref"][0] + 1) % 3, (sd["ref"][0] + 2) % 3]],
+                                         np.int32).reshape(1, 2).copy(), 5, want_tex=True)
+    assert valid.sum() == 0 and ncc[0, 1] == -1.0
+    # bad arguments are reported, never abort
+    with pytest.raises(capi_mod.DpError):
+        ctx.score(sd["pos"][:1], sd["nrm"][:1], sd["ref"][:1], c1["nvis"][:1], c1["vis"][:1], 1)
+    with pytest.raises(capi_mod.DpError):
+        ctx.score(sd["pos"][:1], sd["nrm"][:1], sd["ref"][:1], c1["nvis"][:1], c1["vis"][:1], 33)
