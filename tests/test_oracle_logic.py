@@ -1,0 +1,151 @@
+"""Oracle self-consistency: the parts of the path the reference's own tests do not pin
+(Nelder-Mead, filter off-by-one, organizer, FIFO expansion).  No GPU."""
+import numpy as np
+import pytest
+
+from densepoints_b200 import scenes
+
+
+# ---- cv::DownhillSolver restatement (parity UNPINNED against upstream OpenCV) -------------------
+
+def test_downhill_quadratic_bowl(orc):
+    f = lambda x: float(((x - np.array([0.3, -0.2, 0.1])) ** 2).sum())
+    x, res, fc = orc.downhill(f, [0, 0, 0], [0.02, 0.2, 0.2], max_evals=5000, eps=1e-12)
+    assert np.abs(x - [0.3, -0.2, 0.1]).max() < 1e-4 and res < 1e-8 and 4 < fc <= 5003
+
+
+def test_downhill_rosenbrock_2d(orc):
+    f = lambda x: float(100 * (x[1] - x[0] ** 2) ** 2 + (1 - x[0]) ** 2)
+    x, res, fc = orc.downhill(f, [-1.2, 1.0], [0.5, 0.5], max_evals=20000, eps=1e-14)
+    assert np.abs(x - [1, 1]).max() < 1e-3
+
+
+def test_downhill_initial_simplex_and_constant_function(orc):
+    seen = []
+    f = lambda x: (seen.append(x.copy()), 2.0)[1]
+    x, res, fc = orc.downhill(f, [0, 0, 0], [0.02, 0.2, 0.2])
+    # createInitialSimplex: v0 = x0 - step/2, v_i = x0 + step_i/2 e_i; all equal -> stop at once
+    assert fc == 4 and res == 2.0
+    assert np.allclose(seen[0], [-0.01, -0.1, -0.1])
+    assert np.allclose(seen[1], [0.01, 0, 0]) and np.allclose(seen[2], [0, 0.1, 0])
+    assert np.allclose(seen[3], [0, 0, 0.1])
+    assert np.allclose(x, [0, 0, 0.1])          # `yval <= y[ilo]` keeps the LAST tied vertex
+
+
+def test_downhill_max_evals_cap(orc):
+    f = lambda x: float(np.sin(37 * x[0]) + np.cos(23 * x[1]) + x[2] ** 2 + 3)
+    x, res, fc = orc.downhill(f, [0, 0, 0], [0.5, 0.5, 0.5], max_evals=50, eps=0.0)
+    assert 50 <= fc <= 53                        # the stop test runs once per iteration
+
+
+def test_downhill_decision_tree_trace(orc):
+    """Reflection / expansion / contraction / shrink all occur and every tried point is the
+    documented affine combination of the simplex."""
+    calls = []
+    f = lambda x: (calls.append(x.copy()), float(abs(x[0] - 1) + 3 * abs(x[1] + 2)))[1]
+    x, res, fc = orc.downhill(f, [0, 0], [1.0, 1.0], max_evals=400, eps=1e-9)
+    assert fc == len(calls)
+    assert abs(x[0] - 1) < 1e-3 and abs(x[1] + 2) < 1e-3
+
+
+# ---- filter off-by-one ---------------------------------------------------------------
+
+def test_filter_off_by_one(orc, golden_scoring, golden_views):
+    g = golden_scoring
+    s = 7
+    ncc = orc.score_batch(golden_views, g["pos"], g["nrm"], g["ref"], g["nvis"], g["vis"], s)
+    keep, fnvis, fvis = orc.filter_batch(golden_views, g["pos"], g["nrm"], g["ref"], g["nvis"],
+                                         g["vis"], s, 0.6, 2)
+    saw_shift = False
+    for i in range(len(keep)):
+        nv = g["nvis"][i]
+        vi = list(g["vis"][i, :nv])
+        if nv < 2:
+            assert keep[i] == 0 and fnvis[i] == nv
+            continue
+        # entry k-1 goes iff the score of entry k is low; the last entry always stays
+        exp = [vi[k - 1] for k in range(1, nv) if not (ncc[i, k] < 0.6)] + [vi[-1]]
+        assert list(fvis[i, :fnvis[i]]) == exp
+        assert keep[i] == (len(exp) >= 2)
+        if ncc[i, nv - 1] < 0.6 and all(ncc[i, k] >= 0.6 for k in range(1, nv - 1)):
+            saw_shift = True                      # the bad view survives, a good one is dropped
+    assert saw_shift
+
+
+# ---- homography modes ----------------------------------------------------------------------------
+
+def test_exact_homography_mode_differs_only_at_ties(orc, golden_scoring, golden_views):
+    g = golden_scoring
+    for s in (5, 7, 11, 16):
+        orc.set_homography_mode(0)
+        n0, t0, v0 = orc.score_batch(golden_views, g["pos"], g["nrm"], g["ref"], g["nvis"],
+                                     g["vis"], s, want_tex=True)
+        orc.set_homography_mode(1)
+        try:
+            n1, t1, v1 = orc.score_batch(golden_views, g["pos"], g["nrm"], g["ref"], g["nvis"],
+                                         g["vis"], s, want_tex=True)
+        finally:
+            orc.set_homography_mode(0)
+        assert np.array_equal(v0, v1)
+        diff = (t0 != t1).any(axis=-1)
+        assert diff[..., 1:, :].sum() == 0 and diff[..., 0, 1:].sum() == 0   # only texel (0,0)
+        assert diff.sum() <= 3
+
+
+# ---- organizer + expansion -----------------------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def small_scene(orc):
+    sc = scenes.make_plane_scene(seed=5, n_views=4, width=160, height=120, yaw_spread_deg=14.0)
+    seeds = scenes.make_seeds(sc, 40, seed=6, depth_noise=0.004, tilt_deg=4.0)
+    V = orc.Views(sc.P, sc.images)
+    nvis, vis, _, _ = orc.visibility_batch(V, seeds["pos"], seeds["nrm"], seeds["ref"])
+    return sc, seeds, V, nvis, vis
+
+
+def test_try_insert_semantics(orc, small_scene):
+    sc, seeds, V, nvis, vis = small_scene
+    org = orc.Organizer(V)
+    i = int(np.argmax(nvis))
+    idx, cells = org.try_insert(seeds["pos"][i], seeds["nrm"][i], seeds["ref"][i], vis[i, :nvis[i]])
+    assert idx == 0 and len(cells) == nvis[i] and org.size() == 1
+    for v, r, c in cells:
+        assert org.grid(v)[r, c] == 1
+        assert org.grid(v).shape == (120 // 8, 160 // 8)
+    # the same patch again finds every cell taken -> rejected, store unchanged
+    idx2, cells2 = org.try_insert(seeds["pos"][i], seeds["nrm"][i], seeds["ref"][i], vis[i, :nvis[i]])
+    assert idx2 == -1 and len(cells2) == 0 and org.size() == 1
+    # a patch that wins exactly one cell is rejected but the cell stays consumed
+    org2 = orc.Organizer(V)
+    one = vis[i, :1]
+    idx3, cells3 = org2.try_insert(seeds["pos"][i], seeds["nrm"][i], seeds["ref"][i], one)
+    assert idx3 == -1 and len(cells3) == 1 and org2.size() == 0
+    v, r, c = cells3[0]
+    assert org2.grid(v)[r, c] == 1
+
+
+def test_level_synchronous_expansion_equals_fifo(orc, small_scene):
+    sc, seeds, V, nvis, vis = small_scene
+    prm = orc.default_params(minimum_visible_image=2)
+    orgs = []
+    for mode in ("fifo", "level"):
+        org = orc.Organizer(V, prm)
+        org.set_seeds(seeds["pos"], seeds["nrm"], seeds["ref"], nvis, vis)
+        n0 = org.size()
+        pops = org.expand_fifo(5) if mode == "fifo" else org.expand(5, -1)
+        orgs.append((org, pops, n0))
+    (a, pa, n0), (b, pb, _) = orgs
+    assert pa == pb and a.size() == b.size() and a.size() > n0     # it did expand
+    ea, eb = a.export(), b.export()
+    for k in ea:
+        assert np.array_equal(ea[k], eb[k]), k
+    for v in range(sc.n_views):
+        assert np.array_equal(a.grid(v), b.grid(v))
+
+
+def test_scene_is_deterministic():
+    a = scenes.make_plane_scene(seed=3, n_views=2, width=64, height=48)
+    b = scenes.make_plane_scene(seed=3, n_views=2, width=64, height=48)
+    assert np.array_equal(a.P, b.P) and all(np.array_equal(x, y) for x, y in zip(a.images, b.images))
+    sa, sb = scenes.make_seeds(a, 10, seed=1), scenes.make_seeds(b, 10, seed=1)
+    assert all(np.array_equal(sa[k], sb[k]) for k in sa)
