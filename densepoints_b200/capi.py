@@ -52,10 +52,11 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise DpError(f"{LIB_PATH} is missing: run __graft_entry__.build() "
+        path = os.environ.get("DENSEPOINTS_CUDA_LIB", LIB_PATH)   # tuning builds only
+        if not os.path.exists(path):
+            raise DpError(f"{path} is missing: run __graft_entry__.build() "
                           "(there is no CPU fallback for the CUDA path)")
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(path)
         L.dp_last_error.restype = C.c_char_p
         L.dp_last_error.argtypes = [C.c_void_p]
         L.dp_launch_count.restype = C.c_int64

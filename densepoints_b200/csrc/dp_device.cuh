@@ -128,84 +128,128 @@ struct DpTexels<NPASS, false> {
   }
 };
 
-// The texture of one view: gray value of every texel owned by this lane
-// (g[j], 0..255), optionally the BGR texels themselves.  Returns false where the
-// reference pushes an empty cv::Mat (corner outside, ROI <= 0, degenerate quad).
-// `tile` is this warp's shared-memory staging buffer of tile_cap pixels.
-template <int NPASS, bool WRITE_TEX>
-__device__ __forceinline__ bool dp_view_texture(const DpViewDev *__restrict__ V, int s, int npx,
-                                                const DpFrame &f, const DpTexels<NPASS> &tx,
-                                                uint32_t *tile, int tile_cap, int lane,
-                                                int (&g)[NPASS], uint8_t *__restrict__ tex_out) {
-  // ---- corners (patch.cpp:119-135): lane&3 = corner (-,-) (+,-) (+,+) (-,+) ------------
-  const int c = lane & 3;
-  const double sgx = (c == 1 || c == 2) ? 1.0 : -1.0;
-  const double sgy = (c >= 2) ? 1.0 : -1.0;
-  double X0 = xadd(xadd(f.p[0], sgx * f.ax[0]), sgy * f.ay[0]);
-  double X1 = xadd(xadd(f.p[1], sgx * f.ax[1]), sgy * f.ay[1]);
-  double X2 = xadd(xadd(f.p[2], sgx * f.ax[2]), sgy * f.ay[2]);
-  double u, v;
-  dp_project(V->P, X0, X1, X2, u, v);
-  const int W = V->width, H = V->height;
-  bool in = (u > 0) && (u < (double)W) && (v > 0) && (v < (double)H);  // IsPointInside
-  if (!__all_sync(DP_FULL, in)) return false;
-  // ---- ROI: tl = min ceil, br = max floor (patch.cpp:126-147) ---------------------------
-  int tlx = (int)ceil(u), tly = (int)ceil(v), brx = (int)floor(u), bry = (int)floor(v);
-#pragma unroll
-  for (int o = 1; o <= 2; o <<= 1) {
-    tlx = min(tlx, __shfl_xor_sync(DP_FULL, tlx, o));
-    tly = min(tly, __shfl_xor_sync(DP_FULL, tly, o));
-    brx = max(brx, __shfl_xor_sync(DP_FULL, brx, o));
-    bry = max(bry, __shfl_xor_sync(DP_FULL, bry, o));
-  }
-  tlx = min(tlx, W); tly = min(tly, H); brx = max(brx, 0); bry = max(bry, 0);
-  const int rw = brx - tlx, rh = bry - tly;
-  if (rw <= 0 || rh <= 0) return false;  // optimization.cpp:45
-  // cv::Point2f, then `-= roi.x` in fp32 (patch.cpp:134, 148-151)
-  float fx = __fsub_rn((float)u, (float)tlx);
-  float fy = __fsub_rn((float)v, (float)tly);
-  double qx0 = (double)__shfl_sync(DP_FULL, fx, 0), qy0 = (double)__shfl_sync(DP_FULL, fy, 0);
-  double qx1 = (double)__shfl_sync(DP_FULL, fx, 1), qy1 = (double)__shfl_sync(DP_FULL, fy, 1);
-  double qx2 = (double)__shfl_sync(DP_FULL, fx, 2), qy2 = (double)__shfl_sync(DP_FULL, fy, 2);
-  double qx3 = (double)__shfl_sync(DP_FULL, fx, 3), qy3 = (double)__shfl_sync(DP_FULL, fy, 3);
-  // ---- homography (patch.cpp:153-161 + cv::warpPerspective's inversion) -----------------
-  // cv::findHomography on 4 points is the exact projective map quad -> [0,s]^2 and
-  // warpPerspective uses its inverse; that inverse (cell -> quad) has the closed form
-  // below (unit square -> quad), so no 9x9 eigen-solve and no 3x3 inversion are needed.
-  double sxq = qx0 - qx1 + qx2 - qx3, syq = qy0 - qy1 + qy2 - qy3;
-  double dx1 = qx1 - qx2, dx2 = qx3 - qx2, dy1 = qy1 - qy2, dy2 = qy3 - qy2;
-  double den = dx1 * dy2 - dx2 * dy1;
-  if (!(den != 0.0)) return false;
-  double rden = 1.0 / den;
-  double gq = (sxq * dy2 - dx2 * syq) * rden;
-  double hq = (dx1 * syq - sxq * dy1) * rden;
+// ---------------------------------------------------------------------------------------
+// Phase A: per-view set-up, batched across the warp.
+//
+// Everything that happens once per (patch, view) -- four corner projections, inside test,
+// ROI, the cell -> quad projective map -- is scalar work.  Doing it with all 32 lanes for one
+// view at a time wastes 31/32 of the machine, so it is batched instead: lane = 4*slot +
+// corner handles one corner of one of 8 views per pass, the four lanes of a slot share
+// their results with width-4 shuffles and derive the view's map, and lane 4*slot writes a
+// DpViewSetup record to shared memory.  Phase B then only reads one record per view.
+
+struct __align__(16) DpViewSetup {
+  double M[8];          // source = (M0 x + M1 y + M2, M3 x + M4 y + M5) / (M6 x + M7 y + 1),
+                        // in 1/32-px units (pre-scaled by INTER_TAB_SIZE), relative to the ROI
+  const uint32_t *src;  // first pixel of the ROI (packed BGRx)
+  int pitch, rw, rh;    // image pitch (pixels), ROI width / height
+  int ok;               // 0 where the reference pushes an empty cv::Mat
+  float inv_rw;         // 1 / rw for the staging loop
+  int pad;
+};
+static_assert(sizeof(DpViewSetup) == 96, "DpViewSetup layout");
+
+#define DP_ROUND 16  // views whose set-up records are resident at once (per warp)
+
+__device__ __forceinline__ void dp_setup_views(const DpViewDev *__restrict__ views, int n_views,
+                                               const int32_t *vis, int kcount, int s,
+                                               const DpFrame &f, DpViewSetup *recs, int lane) {
+  const int c = lane & 3, slot = lane >> 2;
+  const double sgx = (c == 1 || c == 2) ? 1.0 : -1.0;  // corners (-,-) (+,-) (+,+) (-,+),
+  const double sgy = (c >= 2) ? 1.0 : -1.0;            // patch.cpp:119-123
+  const double X0 = xadd(xadd(f.p[0], sgx * f.ax[0]), sgy * f.ay[0]);
+  const double X1 = xadd(xadd(f.p[1], sgx * f.ax[1]), sgy * f.ay[1]);
+  const double X2 = xadd(xadd(f.p[2], sgx * f.ax[2]), sgy * f.ay[2]);
   const double inv_s = 1.0 / (double)s;
-  // source = (M0 x + M1 y + M2, M3 x + M4 y + M5) / (M6 x + M7 y + 1), pre-scaled by the
-  // 1/32-px factor INTER_TAB_SIZE
-  const double M0 = 32.0 * (qx1 - qx0 + gq * qx1) * inv_s, M1 = 32.0 * (qx3 - qx0 + hq * qx3) * inv_s;
-  const double M2 = 32.0 * qx0;
-  const double M3 = 32.0 * (qy1 - qy0 + gq * qy1) * inv_s, M4 = 32.0 * (qy3 - qy0 + hq * qy3) * inv_s;
-  const double M5 = 32.0 * qy0;
-  const double M6 = gq * inv_s, M7 = hq * inv_s;
-  if (!(isfinite(M0) && isfinite(M1) && isfinite(M3) && isfinite(M4) && isfinite(M6) &&
-        isfinite(M7)))
-    return false;
-  // ---- stage the ROI into shared memory (row-coalesced) ---------------------------------
-  const uint32_t *__restrict__ src = V->img + (size_t)tly * V->pitch_px + tlx;
-  const int pitch = V->pitch_px;
+#pragma unroll 1
+  for (int base = 0; base < kcount; base += 8) {
+    const int k = base + slot;
+    const bool active = k < kcount;
+    const int vid = active ? vis[k] : -1;
+    const bool inr = active && f.ok && vid >= 0 && vid < n_views;
+    const DpViewDev *V = views + (inr ? vid : 0);
+    double u, v;
+    dp_project(V->P, X0, X1, X2, u, v);
+    const int W = V->width, H = V->height;
+    const bool in = inr && (u > 0) && (u < (double)W) && (v > 0) && (v < (double)H);
+    const unsigned inm = __ballot_sync(DP_FULL, in);
+    const bool all_in = ((inm >> (lane & ~3)) & 0xfu) == 0xfu;  // any corner outside -> empty
+    // ROI: tl = min ceil, br = max floor over the 4 corners (patch.cpp:126-147)
+    int tlx = __double2int_ru(u), tly = __double2int_ru(v);
+    int brx = __double2int_rd(u), bry = __double2int_rd(v);
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      tlx = min(tlx, __shfl_xor_sync(DP_FULL, tlx, o));
+      tly = min(tly, __shfl_xor_sync(DP_FULL, tly, o));
+      brx = max(brx, __shfl_xor_sync(DP_FULL, brx, o));
+      bry = max(bry, __shfl_xor_sync(DP_FULL, bry, o));
+    }
+    tlx = min(tlx, W); tly = min(tly, H); brx = max(brx, 0); bry = max(bry, 0);
+    const int rw = brx - tlx, rh = bry - tly;
+    // cv::Point2f, then `-= roi.x` in fp32 (patch.cpp:134, 148-151)
+    const float fx = __fsub_rn((float)u, (float)tlx);
+    const float fy = __fsub_rn((float)v, (float)tly);
+    const double qx0 = (double)__shfl_sync(DP_FULL, fx, 0, 4), qy0 = (double)__shfl_sync(DP_FULL, fy, 0, 4);
+    const double qx1 = (double)__shfl_sync(DP_FULL, fx, 1, 4), qy1 = (double)__shfl_sync(DP_FULL, fy, 1, 4);
+    const double qx2 = (double)__shfl_sync(DP_FULL, fx, 2, 4), qy2 = (double)__shfl_sync(DP_FULL, fy, 2, 4);
+    const double qx3 = (double)__shfl_sync(DP_FULL, fx, 3, 4), qy3 = (double)__shfl_sync(DP_FULL, fy, 3, 4);
+    // cv::findHomography on 4 points is the exact projective map quad -> [0,s]^2 and
+    // cv::warpPerspective uses its inverse; that inverse (cell -> quad) has the closed form
+    // below (unit square -> quadrilateral): no 9x9 eigen-solve, no 3x3 inversion.
+    const double sxq = qx0 - qx1 + qx2 - qx3, syq = qy0 - qy1 + qy2 - qy3;
+    const double dx1 = qx1 - qx2, dx2 = qx3 - qx2, dy1 = qy1 - qy2, dy2 = qy3 - qy2;
+    const double den = dx1 * dy2 - dx2 * dy1;
+    const double rden = 1.0 / den;
+    const double gq = (sxq * dy2 - dx2 * syq) * rden;
+    const double hq = (dx1 * syq - sxq * dy1) * rden;
+    if (c == 0 && active) {
+      DpViewSetup &R = recs[k];
+      R.M[0] = 32.0 * (qx1 - qx0 + gq * qx1) * inv_s;
+      R.M[1] = 32.0 * (qx3 - qx0 + hq * qx3) * inv_s;
+      R.M[2] = 32.0 * qx0;
+      R.M[3] = 32.0 * (qy1 - qy0 + gq * qy1) * inv_s;
+      R.M[4] = 32.0 * (qy3 - qy0 + hq * qy3) * inv_s;
+      R.M[5] = 32.0 * qy0;
+      R.M[6] = gq * inv_s;
+      R.M[7] = hq * inv_s;
+      const bool fin = isfinite(R.M[0]) && isfinite(R.M[1]) && isfinite(R.M[3]) &&
+                       isfinite(R.M[4]) && isfinite(R.M[6]) && isfinite(R.M[7]);
+      const bool ok = all_in && rw > 0 && rh > 0 && (den != 0.0) && fin;  // optimization.cpp:45
+      R.src = V->img + (ok ? (size_t)tly * V->pitch_px + tlx : 0);
+      R.pitch = V->pitch_px;
+      R.rw = rw;
+      R.rh = rh;
+      R.ok = ok ? 1 : 0;
+      R.inv_rw = __fdividef(1.0f, (float)max(rw, 1));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Phase B: the texture of one view from its set-up record: gray value of every texel owned
+// by this lane (g[j], 0..255), optionally the BGR texels themselves.  `tile` is this warp's
+// shared-memory staging buffer of tile_cap pixels.
+template <int NPASS, bool WRITE_TEX>
+__device__ __forceinline__ void dp_view_texture(const DpViewSetup &R, int npx,
+                                                const DpTexels<NPASS> &tx, uint32_t *tile,
+                                                int tile_cap, int lane, int (&g)[NPASS],
+                                                uint8_t *__restrict__ tex_out) {
+  const double M0 = R.M[0], M1 = R.M[1], M2 = R.M[2], M3 = R.M[3], M4 = R.M[4], M5 = R.M[5],
+               M6 = R.M[6], M7 = R.M[7];
+  const uint32_t *__restrict__ src = R.src;
+  const int pitch = R.pitch, rw = R.rw, rh = R.rh;
+  // ---- stage the ROI into shared memory (flat index, row-coalesced 32-bit loads) ----------
   const int area = rw * rh;
   const bool staged = area <= tile_cap;
   if (staged) {
-    __syncwarp();
-    const float inv_w = 1.0f / (float)rw;
+    const float inv_w = R.inv_rw;
     for (int t = lane; t < area; t += 32) {
-      int r = (int)(((float)t + 0.5f) * inv_w);
-      int cidx = t - r * rw;
-      tile[t] = __ldg(src + (size_t)r * pitch + cidx);
+      const int r = (int)(((float)t + 0.5f) * inv_w);
+      tile[t] = __ldg(src + (unsigned)(r * pitch + (t - r * rw)));
     }
     __syncwarp();
   }
-  // ---- warp the texel grid --------------------------------------------------------------
+  // ---- warp the texel grid ------------------------------------------------------------------
 #pragma unroll
   for (int j = 0; j < NPASS; ++j) {
     const int i = lane + 32 * j;
@@ -213,17 +257,17 @@ __device__ __forceinline__ bool dp_view_texture(const DpViewDev *__restrict__ V,
     if (i < npx) {
       double x, y;
       tx.get(j, i, x, y);
-      double Wd = fma(M6, x, fma(M7, y, 1.0));
+      const double Wd = fma(M6, x, fma(M7, y, 1.0));
       double r = dp_rcp(Wd);
       r = (Wd != 0.0) ? r : 0.0;  // W ? INTER_TAB_SIZE / W : 0
-      double fX = fma(M0, x, fma(M1, y, M2)) * r;
-      double fY = fma(M3, x, fma(M4, y, M5)) * r;
-      int Xi = __double2int_rn(fX);  // saturate_cast<int>(cvRound), half to even
-      int Yi = __double2int_rn(fY);
-      int sx = Xi >> 5, axw = Xi & 31;  // INTER_BITS = 5
-      int sy = Yi >> 5, ayw = Yi & 31;
-      int x0 = min(max(sx, 0), rw - 1), x1 = min(max(sx + 1, 0), rw - 1);  // BORDER_REPLICATE
-      int y0 = min(max(sy, 0), rh - 1), y1 = min(max(sy + 1, 0), rh - 1);  // at the ROI edge
+      const double fX = fma(M0, x, fma(M1, y, M2)) * r;
+      const double fY = fma(M3, x, fma(M4, y, M5)) * r;
+      const int Xi = __double2int_rn(fX);  // saturate_cast<int>(cvRound), half to even
+      const int Yi = __double2int_rn(fY);
+      const int sx = Xi >> 5, axw = Xi & 31;  // INTER_BITS = 5
+      const int sy = Yi >> 5, ayw = Yi & 31;
+      const int x0 = min(max(sx, 0), rw - 1), x1 = min(max(sx + 1, 0), rw - 1);  // BORDER_REPLICATE
+      const int y0 = min(max(sy, 0), rh - 1), y1 = min(max(sy + 1, 0), rh - 1);  // at the ROI edge
       uint32_t p00, p01, p10, p11;
       if (staged) {
         p00 = tile[y0 * rw + x0]; p01 = tile[y0 * rw + x1];
@@ -236,76 +280,56 @@ __device__ __forceinline__ bool dp_view_texture(const DpViewDev *__restrict__ V,
       // separable form of the 15-bit weights (32-ax)(32-ay)*32 ...: exact in integers,
       // (sum*32 + 2^14) >> 15 == (sum + 2^9) >> 10.
       const uint32_t wx1 = (uint32_t)axw, wx0 = 32u - wx1, wy1 = (uint32_t)ayw, wy0 = 32u - wy1;
-      uint32_t br0 = (p00 & 0x00ff00ffu) * wx0 + (p01 & 0x00ff00ffu) * wx1;  // B | R<<16
-      uint32_t br1 = (p10 & 0x00ff00ffu) * wx0 + (p11 & 0x00ff00ffu) * wx1;
-      uint32_t g0 = ((p00 >> 8) & 0xffu) * wx0 + ((p01 >> 8) & 0xffu) * wx1;
-      uint32_t g1 = ((p10 >> 8) & 0xffu) * wx0 + ((p11 >> 8) & 0xffu) * wx1;
-      uint32_t B = ((br0 & 0xffffu) * wy0 + (br1 & 0xffffu) * wy1 + 512u) >> 10;
-      uint32_t R = ((br0 >> 16) * wy0 + (br1 >> 16) * wy1 + 512u) >> 10;
-      uint32_t G = (g0 * wy0 + g1 * wy1 + 512u) >> 10;
+      const uint32_t br0 = (p00 & 0x00ff00ffu) * wx0 + (p01 & 0x00ff00ffu) * wx1;  // B | R<<16
+      const uint32_t br1 = (p10 & 0x00ff00ffu) * wx0 + (p11 & 0x00ff00ffu) * wx1;
+      const uint32_t g0 = ((p00 >> 8) & 0xffu) * wx0 + ((p01 >> 8) & 0xffu) * wx1;
+      const uint32_t g1 = ((p10 >> 8) & 0xffu) * wx0 + ((p11 >> 8) & 0xffu) * wx1;
+      const uint32_t B = ((br0 & 0xffffu) * wy0 + (br1 & 0xffffu) * wy1 + 512u) >> 10;
+      const uint32_t Rr = ((br0 >> 16) * wy0 + (br1 >> 16) * wy1 + 512u) >> 10;
+      const uint32_t G = (g0 * wy0 + g1 * wy1 + 512u) >> 10;
       // cv::cvtColor(BGR2GRAY), 8U: 15-bit fixed point
-      g[j] = (int)((3735u * B + 19235u * G + 9798u * R + (1u << 14)) >> 15);
+      g[j] = (int)((3735u * B + 19235u * G + 9798u * Rr + (1u << 14)) >> 15);
       if (WRITE_TEX) {
         tex_out[3 * i + 0] = (uint8_t)B;
         tex_out[3 * i + 1] = (uint8_t)G;
-        tex_out[3 * i + 2] = (uint8_t)R;
+        tex_out[3 * i + 2] = (uint8_t)Rr;
       }
     }
   }
-  return true;
+  if (staged) __syncwarp();  // the tile may be overwritten by the next view
 }
 
-// Zero-mean NCC state of the anchor texture (NCCScore on textures[0]).
+// Integer moments of the gray texels held by the warp (exact; cv::meanStdDev's sums).
 template <int NPASS>
-struct DpAnchor {
-  float d[NPASS];  // fl32(a_i - fl32(mean_a)), `Mat - scalar` on CV_32F
-  double std;      // population sigma (cv::meanStdDev)
-  bool valid;
-};
-
-// cv::meanStdDev on the gray texels held by the warp: integer sums are exact.
-template <int NPASS>
-__device__ __forceinline__ void dp_mean_std(const int (&g)[NPASS], int npx, double &mean,
-                                            double &stdv) {
-  unsigned s1 = 0, s2 = 0;
+__device__ __forceinline__ void dp_moments(const int (&g)[NPASS], unsigned &s1, unsigned &s2) {
+  unsigned a = 0, b = 0;
 #pragma unroll
   for (int j = 0; j < NPASS; ++j) {
-    s1 += (unsigned)g[j];
-    s2 += (unsigned)(g[j] * g[j]);
+    a += (unsigned)g[j];
+    b += (unsigned)(g[j] * g[j]);
   }
-  s1 = __reduce_add_sync(DP_FULL, s1);
-  s2 = __reduce_add_sync(DP_FULL, s2);
-  const double scale = 1.0 / (double)npx;
-  mean = xmul((double)s1, scale);
-  double var = xsub(xmul((double)s2, scale), xmul(mean, mean));
-  stdv = sqrt(var > 0.0 ? var : 0.0);
+  s1 = __reduce_add_sync(DP_FULL, a);
+  s2 = __reduce_add_sync(DP_FULL, b);
 }
 
+// fl32(g_i - fl32(mean)): `Mat - scalar` on CV_32F (error_measurements.cpp:54)
 template <int NPASS>
-__device__ __forceinline__ void dp_set_anchor(const int (&g)[NPASS], int npx, int lane,
-                                              DpAnchor<NPASS> &a) {
-  double mean;
-  dp_mean_std<NPASS>(g, npx, mean, a.std);
-  const float mf = (float)mean;
+__device__ __forceinline__ void dp_centre(const int (&g)[NPASS], unsigned s1, double scale, int npx,
+                                          int lane, float (&d)[NPASS]) {
+  const float mf = (float)xmul((double)s1, scale);
 #pragma unroll
-  for (int j = 0; j < NPASS; ++j) a.d[j] = (lane + 32 * j < npx) ? __fsub_rn((float)g[j], mf) : 0.f;
+  for (int j = 0; j < NPASS; ++j) d[j] = (lane + 32 * j < npx) ? __fsub_rn((float)g[j], mf) : 0.f;
 }
 
-// NCCScore(anchor, this view) (error_measurements.cpp:47-59)
-template <int NPASS>
-__device__ __forceinline__ double dp_ncc(const DpAnchor<NPASS> &a, const int (&g)[NPASS], int npx,
-                                         int lane) {
-  double mean, stdv;
-  dp_mean_std<NPASS>(g, npx, mean, stdv);
-  const float mf = (float)mean;
-  double num = 0.0;
-#pragma unroll
-  for (int j = 0; j < NPASS; ++j) {
-    float db = (lane + 32 * j < npx) ? __fsub_rn((float)g[j], mf) : 0.f;
-    num = xadd(num, xmul((double)a.d[j], (double)db));
-  }
-  num = warp_sum_f64(num);
-  double den = xmul(a.std, stdv);
+// Phase C, one view per lane: NCCScore from the exact moments and the numerator
+// (error_measurements.cpp:47-59): population sigma, clamp 0.1, (num / den) / N.
+__device__ __forceinline__ double dp_ncc_finish(unsigned a1, unsigned a2, unsigned b1, unsigned b2,
+                                                double num, double scale, int npx) {
+  const double ma = xmul((double)a1, scale), mb = xmul((double)b1, scale);
+  const double va = xsub(xmul((double)a2, scale), xmul(ma, ma));
+  const double vb = xsub(xmul((double)b2, scale), xmul(mb, mb));
+  const double sa = sqrt(va > 0.0 ? va : 0.0), sb = sqrt(vb > 0.0 ? vb : 0.0);
+  double den = xmul(sa, sb);
   den = den > 1e-1 ? den : 1e-1;
   return (num / den) / (double)npx;
 }

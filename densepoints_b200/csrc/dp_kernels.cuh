@@ -11,6 +11,13 @@
 #include "dp_device.cuh"
 
 #define DP_WARPS 8  // warps (= patches in flight) per CTA
+// Resident CTAs per SM requested through __launch_bounds__ (= register cap), measured on
+// B200: the score kernel is fastest at 4 CTAs/SM (64 registers) for <= 2 texel passes, the
+// refine kernel at 2 CTAs/SM (128 registers; 3 CTAs spill 600+ bytes and lose 7 %).
+__host__ __device__ constexpr int dp_score_min_ctas(int npass) {
+  return npass <= 2 ? 4 : (npass <= 4 ? 3 : (npass <= 8 ? 2 : 1));
+}
+__host__ __device__ constexpr int dp_refine_min_ctas(int npass) { return npass <= 8 ? 2 : 1; }
 
 struct DpPatchArgs {
   const DpViewDev *views;
@@ -39,45 +46,82 @@ struct DpTileCfg {
   static constexpr int kTilePx = (128 * NPASS < 1024) ? 128 * NPASS : 1024;
 };
 
-// Evaluate all visible views of one patch at (n, p).  For every k >= 1 calls
-// sink(k, score) with NCCScore(texture 0, texture k) (-1 when either is empty).
+// Evaluate all visible views of one patch at (n, p), DP_ROUND views per round:
+//   phase A  batched set-up of the round's views            (dp_setup_views)
+//   phase B  per view: stage ROI, warp the texels, integer moments, NCC numerator
+//   phase C  one view per lane: NCCScore(texture 0, texture k) from the moments
+// After each round sink(k0, kc, score) is called with lane l holding the score of view
+// k0 + l (l < kc; -1 when either texture is empty, error_measurements.cpp:38-40; the entry
+// of view 0 is meaningless).
 template <int NPASS, bool WRITE_TEX, typename Sink>
 __device__ __forceinline__ void dp_eval_views(const DpViewDev *__restrict__ views, int n_views,
-                                              int ref, const int32_t *vis, int nv,
-                                              int s, int npx, const double n[3], const double p[3],
-                                              const DpTexels<NPASS> &tx, uint32_t *tile, int lane,
-                                              uint8_t *tex_base, uint8_t *valid_base, Sink sink) {
+                                              int ref, const int32_t *vis, int nv, int s, int npx,
+                                              const double n[3], const double p[3],
+                                              const DpTexels<NPASS> &tx, uint32_t *tile,
+                                              DpViewSetup *recs, int lane, uint8_t *tex_base,
+                                              uint8_t *valid_base, Sink sink) {
   DpFrame f;
-  const bool ref_ok = (ref >= 0 && ref < n_views);
-  if (ref_ok)
+  if (ref >= 0 && ref < n_views)
     dp_make_frame(views + ref, s, n, p, f);
   else
     f.ok = false;
-  DpAnchor<NPASS> anchor;
-  anchor.valid = false;
-  for (int k = 0; k < nv; ++k) {
-    const int vid = vis[k];
-    int g[NPASS];
-    bool ok = false;
-    if (f.ok && vid >= 0 && vid < n_views)
-      ok = dp_view_texture<NPASS, WRITE_TEX>(views + vid, s, npx, f, tx, tile,
-                                             DpTileCfg<NPASS>::kTilePx, lane, g,
-                                             WRITE_TEX ? tex_base + (size_t)k * npx * 3 : nullptr);
-    if (valid_base != nullptr && lane == 0) valid_base[k] = ok ? 1 : 0;
-    if (k == 0) {
-      anchor.valid = ok;
-      if (ok) dp_set_anchor<NPASS>(g, npx, lane, anchor);
-    } else {
-      double score = -1.0;  // NCCScore on an empty Mat (error_measurements.cpp:38-40)
-      if (ok && anchor.valid) score = dp_ncc<NPASS>(anchor, g, npx, lane);
-      sink(k, score);
+  const double scale = 1.0 / (double)npx;  // cv::meanStdDev: mean = sum * (1/N)
+  float da[NPASS];                          // centred anchor texels (texture 0)
+  unsigned a1 = 0, a2 = 0;
+  bool a_ok = false;
+#pragma unroll 1
+  for (int k0 = 0; k0 < nv; k0 += DP_ROUND) {
+    const int kc = min(DP_ROUND, nv - k0);
+    __syncwarp();
+    dp_setup_views(views, n_views, vis + k0, kc, s, f, recs, lane);
+    __syncwarp();
+    unsigned my1 = 0, my2 = 0;
+    double mynum = 0.0;
+    int myok = 0;
+#pragma unroll 1
+    for (int l = 0; l < kc; ++l) {
+      const DpViewSetup &R = recs[l];
+      const bool ok = R.ok != 0;  // warp-uniform
+      unsigned s1 = 0, s2 = 0;
+      double num = 0.0;
+      if (ok) {
+        int g[NPASS];
+        dp_view_texture<NPASS, WRITE_TEX>(R, npx, tx, tile, DpTileCfg<NPASS>::kTilePx, lane, g,
+                                          WRITE_TEX ? tex_base + (size_t)(k0 + l) * npx * 3
+                                                    : nullptr);
+        dp_moments<NPASS>(g, s1, s2);
+        if (k0 + l == 0) {
+          a1 = s1;
+          a2 = s2;
+          a_ok = true;
+          dp_centre<NPASS>(g, s1, scale, npx, lane, da);
+        } else if (a_ok) {
+          float db[NPASS];
+          dp_centre<NPASS>(g, s1, scale, npx, lane, db);
+#pragma unroll
+          for (int j = 0; j < NPASS; ++j) num = xadd(num, xmul((double)da[j], (double)db[j]));
+          num = warp_sum_f64(num);
+        }
+      }
+      if (lane == l) {
+        my1 = s1;
+        my2 = s2;
+        mynum = num;
+        myok = ok ? 1 : 0;
+      }
     }
+    double score = -1.0;
+    if (lane < kc && k0 + lane >= 1 && myok && a_ok)
+      score = dp_ncc_finish(a1, a2, my1, my2, mynum, scale, npx);
+    if (valid_base != nullptr && lane < kc) valid_base[k0 + lane] = (uint8_t)myok;
+    sink(k0, kc, score);
   }
 }
 
 template <int NPASS, bool WRITE_TEX, bool FILTER>
-__global__ void __launch_bounds__(DP_WARPS * 32) dp_score_kernel(DpScoreArgs a) {
+__global__ void __launch_bounds__(DP_WARPS * 32, dp_score_min_ctas(NPASS)) dp_score_kernel(DpScoreArgs a) {
   __shared__ uint32_t tiles[DP_WARPS][DpTileCfg<NPASS>::kTilePx];
+  __shared__ DpViewSetup recs[DP_WARPS][DP_ROUND];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long i = (long long)blockIdx.x * DP_WARPS + warp;
   if (i >= a.p.n) return;
@@ -95,27 +139,34 @@ __global__ void __launch_bounds__(DP_WARPS * 32) dp_score_kernel(DpScoreArgs a) 
   // FilterByErrorMeasurement's erase loop (optimization.cpp:117-124) erases
   // visible[i - removed] when scores[i] (the score of visible[i+1]) is low; since every
   // erased entry lies before the cursor this is "drop original entry k-1 iff the score of
-  // entry k is low", and the last entry always survives -- evaluated online here.
+  // entry k is low", and the last entry always survives.  Evaluated round by round with a
+  // ballot compaction, in place: a round only writes positions below the entries that later
+  // rounds still have to read.
   int wcur = 0;
-  int prev = nv > 0 ? vis[0] : -1;
   const double thr = a.thr;
+  const unsigned lt = (1u << lane) - 1u;
   dp_eval_views<NPASS, WRITE_TEX>(
-      a.p.views, a.p.n_views, ref, vis, nv, s, npx, n, p, tx, tiles[warp], lane, tex, valid,
-      [&](int k, double score) {
-        if (ncc != nullptr && lane == 0) ncc[k] = (float)score;
+      a.p.views, a.p.n_views, ref, vis, nv, s, npx, n, p, tx, tiles[warp], recs[warp], lane, tex,
+      valid, [&](int k0, int kc, double score) {
+        const int k = k0 + lane;
+        const bool mine = lane < kc && k >= 1;
+        if (ncc != nullptr && mine) ncc[k] = (float)score;
         if (FILTER) {
-          if (!(score < thr)) {
-            if (lane == 0) vis[wcur] = prev;  // wcur <= k-1: entry k is still unread-safe
-            ++wcur;
-          }
-          prev = vis[k];
+          const bool keepf = mine && !(score < thr);
+          const int prev = mine ? vis[k - 1] : -1;
+          const unsigned m = __ballot_sync(DP_FULL, keepf);
+          __syncwarp();
+          if (keepf) vis[wcur + __popc(m & lt)] = prev;
+          wcur += __popc(m);
+          __syncwarp();
         }
       });
   if (FILTER) {
     bool kept = false;
     if (nv >= 2) {  // scores.size() > 0 (optimization.cpp:113)
-      if (lane == 0) vis[wcur] = prev;
+      if (lane == 0) vis[wcur] = vis[nv - 1];
       ++wcur;
+      __syncwarp();
       for (int k = wcur + lane; k < nv; k += 32) vis[k] = -1;
       if (lane == 0) a.p.nvis[i] = wcur;
       kept = wcur >= a.min_visible;  // optimization.cpp:127
@@ -154,59 +205,79 @@ __device__ __forceinline__ void dp_unparametrize(const double *__restrict__ C, c
   n[2] = xadd(xadd(xmul(xmul(ca, sb), n0[0]), xmul(-sa, n0[1])), xmul(xmul(ca, cb), n0[2]));
 }
 
-// Nelder-Mead state of one patch (cv::DownhillSolver, ndim = 3).  Every lane of the
-// owning warp holds the same values in registers; run-time vertex indices (ilo / ihi)
-// are resolved with unrolled selects so nothing is spilled to local memory.
-struct DpSimplex {
-  double P[4][3];  // vertices
-  double y[4];     // objective at the vertices
-  double cs[3];    // coord_sum
-  __device__ __forceinline__ void getP(int v, double o[3]) const {
-#pragma unroll
-    for (int j = 0; j < 3; ++j) o[j] = v == 0 ? P[0][j] : (v == 1 ? P[1][j] : (v == 2 ? P[2][j] : P[3][j]));
+// Nelder-Mead state of one patch (cv::DownhillSolver, ndim = 3), kept "in the lanes":
+// every lane owns one slot = a 3-vector plus a scalar (8 registers), so the whole solver
+// state costs 8 registers per thread instead of ~60 for warp-uniform copies.  Slots are read
+// with shuffles (a few dozen per Nelder-Mead step, against thousands of instructions per
+// objective evaluation).
+struct DpSlots {
+  double x, y, z, v;
+  __device__ __forceinline__ void get3(int slot, double o[3]) const {
+    o[0] = __shfl_sync(DP_FULL, x, slot);
+    o[1] = __shfl_sync(DP_FULL, y, slot);
+    o[2] = __shfl_sync(DP_FULL, z, slot);
   }
-  __device__ __forceinline__ void setP(int v, const double o[3]) {
-#pragma unroll
-    for (int w = 0; w < 4; ++w)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) P[w][j] = (w == v) ? o[j] : P[w][j];
+  __device__ __forceinline__ double getv(int slot) const { return __shfl_sync(DP_FULL, v, slot); }
+  __device__ __forceinline__ void set3(int slot, int lane, const double o[3]) {
+    if (lane == slot) { x = o[0]; y = o[1]; z = o[2]; }
   }
-  __device__ __forceinline__ void setY(int v, double val) {
-#pragma unroll
-    for (int w = 0; w < 4; ++w) y[w] = (w == v) ? val : y[w];
+  __device__ __forceinline__ void setv(int slot, int lane, double val) {
+    if (lane == slot) v = val;
   }
 };
+// slots 0..3: simplex vertices (v = objective there)
+#define SL_PA 4   // accepted reflection point, v = y_alpha
+#define SL_PT 5   // point being evaluated
+#define SL_CS 6   // coord_sum
+#define SL_YS 7   // x = y_lo, y = y_nhi, z = y_hi of the current iteration
+#define SL_N0 8   // patch normal at entry
+#define SL_P0 9   // patch position at entry
+#define SL_C 10   // camera centre of the reference view
 
-__device__ __forceinline__ void dp_coord_sum(DpSimplex &S) {
+// coord_sum = sum of the vertices, accumulated in vertex order (updateCoordSum)
+__device__ __forceinline__ void dp_coord_sum(DpSlots &S, int lane) {
+  double t[3] = {0.0, 0.0, 0.0}, q[3];
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    double t = 0.0;
+  for (int v = 0; v < 4; ++v) {
+    S.get3(v, q);
 #pragma unroll
-    for (int v = 0; v < 4; ++v) t = xadd(t, S.P[v][j]);
-    S.cs[j] = t;
+    for (int j = 0; j < 3; ++j) t[j] = xadd(t[j], q[j]);
   }
+  S.set3(SL_CS, lane, t);
 }
 
-// tryNewPoint / replacePoint: ptry = coord_sum * (1-a)/n - p_hi * ((1-a)/n - a)
-__device__ __forceinline__ void dp_try_point(const DpSimplex &S, int ihi, double alpha_,
-                                             double pt[3]) {
+// tryNewPoint / replacePoint: ptry = coord_sum * (1-a)/n - p_hi * ((1-a)/n - a)  -> SL_PT
+__device__ __forceinline__ void dp_try_point(DpSlots &S, int lane, int ihi, double alpha_) {
   const double al = (1.0 - alpha_) / 3.0;
   const double be = xsub(al, alpha_);
-  double ph[3];
-  S.getP(ihi, ph);
+  double cs[3], ph[3], pt[3];
+  S.get3(SL_CS, cs);
+  S.get3(ihi, ph);
 #pragma unroll
-  for (int j = 0; j < 3; ++j) pt[j] = xsub(xmul(S.cs[j], al), xmul(ph[j], be));
+  for (int j = 0; j < 3; ++j) pt[j] = xsub(xmul(cs[j], al), xmul(ph[j], be));
+  S.set3(SL_PT, lane, pt);
+}
+
+// vertex idx <- halfway to vertex ilo (the shrink step); also becomes the point to evaluate
+__device__ __forceinline__ void dp_shrink_vertex(DpSlots &S, int lane, int idx, int ilo) {
+  double pi[3], pl[3], pt[3];
+  S.get3(idx, pi);
+  S.get3(ilo, pl);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) pt[j] = xmul(0.5, xadd(pi[j], pl[j]));
+  S.set3(idx, lane, pt);
+  S.set3(SL_PT, lane, pt);
 }
 
 template <int NPASS>
-__global__ void __launch_bounds__(DP_WARPS * 32) dp_refine_kernel(DpRefineArgs a) {
+__global__ void __launch_bounds__(DP_WARPS * 32, dp_refine_min_ctas(NPASS)) dp_refine_kernel(DpRefineArgs a) {
   __shared__ uint32_t tiles[DP_WARPS][DpTileCfg<NPASS>::kTilePx];
+  __shared__ DpViewSetup recs[DP_WARPS][DP_ROUND];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = a.p.s, npx = s * s;
   DpTexels<NPASS> tx;
   tx.init(s, lane);
   uint32_t *tile = tiles[warp];
-  DpSimplex S;
   enum { ST_INIT, ST_REFLECT, ST_EXPAND, ST_CONTRACT, ST_SHRINK };
   for (;;) {
     unsigned int iu = 0;
@@ -221,149 +292,172 @@ __global__ void __launch_bounds__(DP_WARPS * 32) dp_refine_kernel(DpRefineArgs a
     const int nv = min(a.p.nvis[i], a.p.vstride);
     const int ref = a.p.ref[i];
     const bool ref_ok = ref >= 0 && ref < a.p.n_views;
-    const double n0[3] = {(double)a.p.nrm[3 * i], (double)a.p.nrm[3 * i + 1],
-                          (double)a.p.nrm[3 * i + 2]};
-    const double p0[3] = {(double)a.p.pos[3 * i], (double)a.p.pos[3 * i + 1],
-                          (double)a.p.pos[3 * i + 2]};
     const int32_t *vis = a.p.vis + (size_t)i * a.p.vstride;
-    const double *C = a.p.views[ref_ok ? ref : 0].center;
-    const double c3[3] = {C[0], C[1], C[2]};
-
-    // createInitialSimplex: v_i = x0 + step_{i-1}/2 e_{i-1}, then v_0 = x0 - step/2; x0 = 0
-#pragma unroll
-    for (int v = 0; v < 4; ++v)
-#pragma unroll
-      for (int j = 0; j < 3; ++j)
-        S.P[v][j] = (v == 0) ? xsub(0.0, xmul(0.5, a.step[j]))
-                             : ((v - 1 == j) ? xadd(0.0, xmul(0.5, a.step[j])) : 0.0);
+    DpSlots S;
+    {
+      // createInitialSimplex: v_i = x0 + step_{i-1}/2 e_{i-1}, then v_0 = x0 - step/2; x0 = 0
+      const double h0 = xmul(0.5, a.step[0]), h1 = xmul(0.5, a.step[1]), h2 = xmul(0.5, a.step[2]);
+      S.x = lane == 0 ? xsub(0.0, h0) : (lane == 1 ? xadd(0.0, h0) : 0.0);
+      S.y = lane == 0 ? xsub(0.0, h1) : (lane == 2 ? xadd(0.0, h1) : 0.0);
+      S.z = lane == 0 ? xsub(0.0, h2) : (lane == 3 ? xadd(0.0, h2) : 0.0);
+      S.v = 0.0;
+      if (lane == SL_PT) { S.x = xsub(0.0, h0); S.y = xsub(0.0, h1); S.z = xsub(0.0, h2); }
+      if (lane == SL_N0) { S.x = (double)a.p.nrm[3 * i]; S.y = (double)a.p.nrm[3 * i + 1]; S.z = (double)a.p.nrm[3 * i + 2]; }
+      if (lane == SL_P0) { S.x = (double)a.p.pos[3 * i]; S.y = (double)a.p.pos[3 * i + 1]; S.z = (double)a.p.pos[3 * i + 2]; }
+      if (lane == SL_C) {
+        const double *C = a.p.views[ref_ok ? ref : 0].center;
+        S.x = C[0]; S.y = C[1]; S.z = C[2];
+      }
+    }
     int state = ST_INIT, idx = 0, fcount = 4;
     int ilo = 0, ihi = 0;
-    double y_lo = 0, y_nhi = 0, y_hi = 0, y_alpha = 0;
-    double pt[3] = {S.P[0][0], S.P[0][1], S.P[0][2]}, pa[3] = {0, 0, 0};
 #pragma unroll 1
     for (;;) {
       // ---- the single objective call site: PatchOptimizationOpenCVFunctor::calc ----------
       double fval = 2.0;  // scores.size() == 0 (optimization_opencv.cpp:30-32)
       if (nv >= 2 && ref_ok) {
-        double n[3], p[3];
+        double pt[3], n0[3], p0[3], c3[3], n[3], p[3];
+        S.get3(SL_PT, pt);
+        S.get3(SL_N0, n0);
+        S.get3(SL_P0, p0);
+        S.get3(SL_C, c3);
         dp_unparametrize(c3, n0, p0, pt[0], pt[1], pt[2], n, p);
         double sum = 0.0;
-        dp_eval_views<NPASS, false>(a.p.views, a.p.n_views, ref, vis, nv, s, npx, n, p, tx, tile,
-                                    lane, nullptr, nullptr,
-                                    [&](int, double score) { sum = xadd(sum, xsub(1.0, score)); });
+        dp_eval_views<NPASS, false>(
+            a.p.views, a.p.n_views, ref, vis, nv, s, npx, n, p, tx, tile, recs[warp], lane,
+            nullptr, nullptr, [&](int k0, int kc, double score) {
+              // std::accumulate of (1 - NCC) in view order (optimization_opencv.cpp:24, 34)
+              const double term = xsub(1.0, score);
+              for (int l = (k0 == 0 ? 1 : 0); l < kc; ++l)
+                sum = xadd(sum, __shfl_sync(DP_FULL, term, l));
+            });
         fval = sum / (double)(nv - 1);
       }
       // ---- consume it according to the Nelder-Mead state ---------------------------------
       bool decide = false;
       if (state == ST_INIT) {
-        S.setY(idx, fval);
+        S.setv(idx, lane, fval);
         if (++idx < 4) {
-          S.getP(idx, pt);
+          double q[3];
+          S.get3(idx, q);
+          S.set3(SL_PT, lane, q);
         } else {
-          dp_coord_sum(S);
+          dp_coord_sum(S, lane);
           decide = true;
         }
       } else if (state == ST_REFLECT) {
-        y_alpha = fval;
-        pa[0] = pt[0]; pa[1] = pt[1]; pa[2] = pt[2];
-        if (y_alpha < y_nhi) {
-          if (y_alpha < y_lo) {  // try twice as far
+        const double y_lo = __shfl_sync(DP_FULL, S.x, SL_YS), y_nhi = __shfl_sync(DP_FULL, S.y, SL_YS);
+        double q[3];
+        S.get3(SL_PT, q);
+        S.set3(SL_PA, lane, q);
+        S.setv(SL_PA, lane, fval);  // y_alpha
+        if (fval < y_nhi) {
+          if (fval < y_lo) {  // better than the best: try twice as far
             state = ST_EXPAND;
-            dp_try_point(S, ihi, -2.0, pt);
+            dp_try_point(S, lane, ihi, -2.0);
             ++fcount;
           } else {
+            S.set3(ihi, lane, q);  // replacePoint(alpha = -1)
+            S.setv(ihi, lane, fval);
+            dp_coord_sum(S, lane);
             decide = true;
           }
         } else {
           state = ST_CONTRACT;
-          dp_try_point(S, ihi, 0.5, pt);
+          dp_try_point(S, lane, ihi, 0.5);
           ++fcount;
         }
-        if (decide) {  // replacePoint(alpha)
-          S.setP(ihi, pa);
-          S.setY(ihi, y_alpha);
-          dp_coord_sum(S);
-        }
       } else if (state == ST_EXPAND) {
+        double y_alpha = S.getv(SL_PA);
+        double q[3];
         if (fval < y_alpha) {
           y_alpha = fval;
-          pa[0] = pt[0]; pa[1] = pt[1]; pa[2] = pt[2];
+          S.get3(SL_PT, q);
+        } else {
+          S.get3(SL_PA, q);
         }
-        S.setP(ihi, pa);
-        S.setY(ihi, y_alpha);
-        dp_coord_sum(S);
+        S.set3(ihi, lane, q);
+        S.setv(ihi, lane, y_alpha);
+        dp_coord_sum(S, lane);
         decide = true;
       } else if (state == ST_CONTRACT) {
+        const double y_hi = __shfl_sync(DP_FULL, S.z, SL_YS);
         if (fval < y_hi) {
-          S.setP(ihi, pt);
-          S.setY(ihi, fval);
-          dp_coord_sum(S);
+          double q[3];
+          S.get3(SL_PT, q);
+          S.set3(ihi, lane, q);
+          S.setv(ihi, lane, fval);
+          dp_coord_sum(S, lane);
           decide = true;
         } else {  // shrink every vertex but the best halfway towards it
           state = ST_SHRINK;
           idx = (ilo == 0) ? 1 : 0;
-          double pi[3], pl[3];
-          S.getP(idx, pi);
-          S.getP(ilo, pl);
-#pragma unroll
-          for (int j = 0; j < 3; ++j) pt[j] = xmul(0.5, xadd(pi[j], pl[j]));
-          S.setP(idx, pt);
+          dp_shrink_vertex(S, lane, idx, ilo);
         }
       } else {  // ST_SHRINK
-        S.setY(idx, fval);
+        S.setv(idx, lane, fval);
         ++idx;
         if (idx == ilo) ++idx;
         if (idx < 4) {
-          double pi[3], pl[3];
-          S.getP(idx, pi);
-          S.getP(ilo, pl);
-#pragma unroll
-          for (int j = 0; j < 3; ++j) pt[j] = xmul(0.5, xadd(pi[j], pl[j]));
-          S.setP(idx, pt);
+          dp_shrink_vertex(S, lane, idx, ilo);
         } else {
           fcount += 3;
-          dp_coord_sum(S);
+          dp_coord_sum(S, lane);
           decide = true;
         }
       }
       if (!decide) continue;
       // ---- find worst, next-to-worst and best vertices; stop test ------------------------
+      double yv[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) yv[v] = S.getv(v);
       int inhi;
-      double ylo = S.y[0], yhi, ynhi;
+      double ylo = yv[0], yhi, ynhi;
       ilo = 0;
-      if (S.y[0] > S.y[1]) { ihi = 0; yhi = S.y[0]; inhi = 1; ynhi = S.y[1]; }
-      else { ihi = 1; yhi = S.y[1]; inhi = 0; ynhi = S.y[0]; }
+      if (yv[0] > yv[1]) { ihi = 0; yhi = yv[0]; inhi = 1; ynhi = yv[1]; }
+      else { ihi = 1; yhi = yv[1]; inhi = 0; ynhi = yv[0]; }
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
-        const double yv = S.y[v];
-        if (yv <= ylo) { ilo = v; ylo = yv; }
-        if (yv > yhi) { inhi = ihi; ynhi = yhi; ihi = v; yhi = yv; }
-        else if (yv > ynhi && v != ihi) { inhi = v; ynhi = yv; }
+        const double yc = yv[v];
+        if (yc <= ylo) { ilo = v; ylo = yc; }
+        if (yc > yhi) { inhi = ihi; ynhi = yhi; ihi = v; yhi = yc; }
+        else if (yc > ynhi && v != ihi) { inhi = v; ynhi = yc; }
       }
       if (ilo == inhi || ilo == ihi) {
 #pragma unroll
         for (int v = 3; v >= 0; --v)  // ascending search, first match wins
-          if (S.y[v] == ylo && v != ihi && v != inhi) ilo = v;
+          if (yv[v] == ylo && v != ihi && v != inhi) ilo = v;
       }
       const double error = fabs(xsub(yhi, ylo));
-      double range = 0.0;
+      // range = max over coordinates of (max - min) over the 4 vertices = lanes 0..3 (the
+      // xor-1/2 butterflies stay inside that group; other groups compute garbage, unused)
+      double range;
+      {
+        double mnx = S.x, mxx = S.x, mny = S.y, mxy = S.y, mnz = S.z, mxz = S.z;
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        double mn = S.P[0][j], mx = S.P[0][j];
-#pragma unroll
-        for (int v = 1; v < 4; ++v) { mn = fmin(mn, S.P[v][j]); mx = fmax(mx, S.P[v][j]); }
-        range = fmax(range, fabs(xsub(mx, mn)));
+        for (int o = 1; o <= 2; o <<= 1) {
+          mnx = fmin(mnx, __shfl_xor_sync(DP_FULL, mnx, o));
+          mxx = fmax(mxx, __shfl_xor_sync(DP_FULL, mxx, o));
+          mny = fmin(mny, __shfl_xor_sync(DP_FULL, mny, o));
+          mxy = fmax(mxy, __shfl_xor_sync(DP_FULL, mxy, o));
+          mnz = fmin(mnz, __shfl_xor_sync(DP_FULL, mnz, o));
+          mxz = fmax(mxz, __shfl_xor_sync(DP_FULL, mxz, o));
+        }
+        range = fmax(fabs(xsub(mxx, mnx)), fmax(fabs(xsub(mxy, mny)), fabs(xsub(mxz, mnz))));
+        range = __shfl_sync(DP_FULL, range, 0);
       }
       if (range <= a.eps || error <= a.eps || fcount >= a.max_evals) break;
-      y_lo = ylo; y_nhi = ynhi; y_hi = yhi;
+      if (lane == SL_YS) { S.x = ylo; S.y = ynhi; S.z = yhi; }
       state = ST_REFLECT;  // reflect the worst point about the centroid of the others
-      dp_try_point(S, ihi, -1.0, pt);
+      dp_try_point(S, lane, ihi, -1.0);
       ++fcount;
     }
     // best vertex -> x; UnparametrizePatch; SetNormal / SetPosition store fp32
-    double xb[3];
-    S.getP(ilo, xb);
-    double n[3], p[3];
+    double xb[3], n0[3], p0[3], c3[3], n[3], p[3];
+    S.get3(ilo, xb);
+    S.get3(SL_N0, n0);
+    S.get3(SL_P0, p0);
+    S.get3(SL_C, c3);
     dp_unparametrize(c3, n0, p0, xb[0], xb[1], xb[2], n, p);
     if (lane < 3) {
       const double nv_ = lane == 0 ? n[0] : (lane == 1 ? n[1] : n[2]);

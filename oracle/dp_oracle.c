@@ -402,6 +402,31 @@ static int g_homography_mode = 0;
 void orc_set_homography_mode(int mode) { g_homography_mode = mode; }
 int orc_get_homography_mode(void) { return g_homography_mode; }
 
+/* cv::pyrDown on CV_8UC3 (the build's pyramid extension; the reference has no pyramid,
+ * modules/image/Image.h:1-7): separable [1 4 6 4 1]/16, BORDER_REFLECT_101, output
+ * ((w+1)/2, (h+1)/2), exact integer accumulation, (sum + 128) >> 8. */
+static int reflect101(int i, int n) {
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
+  return i;
+}
+void orc_pyrdown(const uint8_t *src, size_t sstride, int w, int h, uint8_t *dst, size_t dstride) {
+  static const int k[5] = {1, 4, 6, 4, 1};
+  int dw = (w + 1) / 2, dh = (h + 1) / 2;
+  for (int y = 0; y < dh; ++y)
+    for (int x = 0; x < dw; ++x)
+      for (int c = 0; c < 3; ++c) {
+        int sum = 0;
+        for (int dy = -2; dy <= 2; ++dy) {
+          const uint8_t *row = src + (size_t)reflect101(2 * y + dy, h) * sstride;
+          int r = 0;
+          for (int dx = -2; dx <= 2; ++dx) r += k[dx + 2] * row[3 * reflect101(2 * x + dx, w) + c];
+          sum += k[dy + 2] * r;
+        }
+        dst[(size_t)y * dstride + 3 * x + c] = (uint8_t)((sum + 128) >> 8);
+      }
+}
+
 /* cv::DownhillSolver::minimize (OpenCV >= 3.0 core/downhill_simplex.cpp), called
  * at optimization_opencv.cpp:63.  PARITY UNPINNED against upstream: the solver's
  * source is neither in the reference tree nor in this image; this restates the

@@ -97,6 +97,8 @@ int orc_get_homography_mode(void);
 int orc_cell_to_quad(const float quad[8], int s, double M[9]);
 int orc_patch_quad(const orc_view *v, const double pos[3], const double ax[3], const double ay[3],
                    float pts[8], int roi[4]);
+/* cv::pyrDown, CV_8UC3 (pyramid extension; pinned against cv2 golden vectors). */
+void orc_pyrdown(const uint8_t *src, size_t sstride, int w, int h, uint8_t *dst, size_t dstride);
 /* cv::cvtColor(BGR2GRAY) for one pixel (OpenCV 4.x 15-bit constants). */
 int orc_gray(int b, int g, int r);
 /* cv::DownhillSolver::minimize restated (ndim <= 8). Returns f(best); x <- best. */

@@ -149,6 +149,15 @@ def warp_perspective(src, H, s):
     return out
 
 
+def pyrdown(img):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape[:2]
+    out = np.zeros(((h + 1) // 2, (w + 1) // 2, 3), np.uint8)
+    lib().orc_pyrdown(_p(img), C.c_size_t(img.strides[0]), C.c_int(w), C.c_int(h), _p(out),
+                      C.c_size_t(out.strides[0]))
+    return out
+
+
 def gray(b, g, r):
     return lib().orc_gray(C.c_int(int(b)), C.c_int(int(g)), C.c_int(int(r)))
 
@@ -253,6 +262,23 @@ def compute_color(views: Views, pos):
     for i in range(pos.shape[0]):
         lib().orc_compute_color(views.arr, C.c_int(views.n), _p(pos[i]), _p(out[i]))
     return out
+
+
+def expand_patch(views: Views, prm, cell_size, pos, nrm, ref, pvis):
+    """Expand::ExpandPatch (expand.cpp:103-143): accepted children of one parent as a list of
+    (direction, pos f32[3], nrm f32[3], vis i32[nvis])."""
+    pos, nrm, pvis = _f32(pos), _f32(nrm), _i32(pvis)
+    out_pos = np.zeros((4, 3), np.float32)
+    out_nrm = np.zeros((4, 3), np.float32)
+    out_nvis = np.zeros(4, np.int32)
+    out_vis = np.full((4, views.n), -1, np.int32)
+    dirs = np.zeros(4, np.int32)
+    cnt = lib().orc_expand_patch(views.arr, C.c_int(views.n), C.byref(prm), C.c_int(cell_size),
+                                 _p(pos), _p(nrm), C.c_int(int(ref)), _p(pvis),
+                                 C.c_int(pvis.size), _p(out_pos), _p(out_nrm), _p(out_nvis),
+                                 _p(out_vis), _p(dirs))
+    return [(int(dirs[k]), out_pos[k].copy(), out_nrm[k].copy(), out_vis[k, :out_nvis[k]].copy())
+            for k in range(cnt)]
 
 
 class Organizer:

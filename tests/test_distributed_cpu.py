@@ -1,0 +1,115 @@
+"""N>1 host logic on CPU: two gloo ranks run the multi-GPU expansion driver
+(densepoints_b200/distributed.py) over an oracle-backed level backend; both must end with
+the store and grids of the single-process 1-thread FIFO."""
+import os
+import tempfile
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from densepoints_b200 import distributed as dd
+from densepoints_b200 import scenes
+
+CELL = 5
+
+
+def _scene():
+    sc = scenes.make_plane_scene(seed=5, n_views=4, width=160, height=120, yaw_spread_deg=14.0)
+    seeds = scenes.make_seeds(sc, 40, seed=6, depth_noise=0.004, tilt_deg=4.0)
+    return sc, seeds
+
+
+class OracleLevelBackend:
+    """Same three steps as CudaLevelBackend, computed with the CPU oracle."""
+
+    def __init__(self, orc, V, prm, seeds, nvis, vis):
+        self.orc, self.V, self.prm = orc, V, prm
+        self.org = orc.Organizer(V, prm)
+        self.org.set_seeds(seeds["pos"], seeds["nrm"], seeds["ref"], nvis, vis)
+        self.begin = 0
+        self.words = 9 + V.n
+
+    def frontier(self):
+        return self.begin, self.org.size()
+
+    def local(self, cell_size, rank, world, rov, max_records):
+        st = self.org.export()
+        rows = []
+        for i in range(self.begin, self.org.size()):
+            if st["nvis"][i] < 2 or (world > 1 and rov[st["ref"][i]] != rank):
+                continue
+            kids = self.orc.expand_patch(self.V, self.prm, cell_size, st["pos"][i], st["nrm"][i],
+                                         st["ref"][i], st["vis"][i, :st["nvis"][i]])
+            for d, p, n, v in kids:
+                row = np.full(self.words, -1, np.int32)
+                row[0] = (i - self.begin) * 4 + d
+                row[1] = st["ref"][i]
+                row[2] = len(v)
+                row[3:6] = p.view(np.int32)
+                row[6:9] = n.view(np.int32)
+                row[9:9 + len(v)] = v
+                rows.append(row)
+        buf = torch.from_numpy(np.array(rows, np.int32).reshape(-1, self.words))
+        return buf, len(rows)
+
+    def commit(self, records, total):
+        n0 = self.org.size()
+        rec = records.numpy()[:total]
+        for row in rec[np.argsort(rec[:, 0], kind="stable")]:
+            self.org.try_insert(row[3:6].copy().view(np.float32), row[6:9].copy().view(np.float32),
+                                int(row[1]), row[9:9 + row[2]])
+        self.begin = n0
+        return self.org.size() - n0
+
+
+def _worker(rank, world, port, outdir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as orc
+    sc, seeds = _scene()
+    V = orc.Views(sc.P, sc.images)
+    prm = orc.default_params(minimum_visible_image=2)
+    nvis, vis, _, _ = orc.visibility_batch(V, seeds["pos"], seeds["nrm"], seeds["ref"])
+    be = OracleLevelBackend(orc, V, prm, seeds, nvis, vis)
+    rov = dd.partition_views(seeds["ref"], sc.n_views, world)
+    stats = dd.expand_distributed(be, CELL, -1, rank, world, rov)
+    ex = be.org.export()
+    np.savez(os.path.join(outdir, f"rank{rank}.npz"), **ex,
+             grids=np.concatenate([be.org.grid(v).ravel() for v in range(sc.n_views)]),
+             local=stats["local_records"], passed=stats["passed"])
+    dist.destroy_process_group()
+
+
+def test_partition_views_is_contiguous_and_balanced():
+    ref = np.repeat(np.arange(8), [10, 10, 10, 10, 40, 40, 40, 40])
+    rov = dd.partition_views(ref, 8, 2)
+    assert (np.diff(rov) >= 0).all() and set(rov) == {0, 1}
+    load = [np.isin(ref, np.where(rov == r)[0]).sum() for r in range(2)]
+    assert max(load) <= 0.65 * len(ref)
+    assert (dd.partition_views(ref, 8, 1) == 0).all()
+
+
+def test_two_rank_expansion_matches_single_process_fifo(orc):
+    sc, seeds = _scene()
+    V = orc.Views(sc.P, sc.images)
+    prm = orc.default_params(minimum_visible_image=2)
+    nvis, vis, _, _ = orc.visibility_batch(V, seeds["pos"], seeds["nrm"], seeds["ref"])
+    ref_org = orc.Organizer(V, prm)
+    ref_org.set_seeds(seeds["pos"], seeds["nrm"], seeds["ref"], nvis, vis)
+    n_seed = ref_org.size()
+    ref_org.expand_fifo(CELL)
+    want = ref_org.export()
+    assert ref_org.size() > n_seed
+    with tempfile.TemporaryDirectory() as d:
+        port = 29500 + (os.getpid() % 2000)
+        mp.spawn(_worker, args=(2, port, d), nprocs=2, join=True)
+        got = [dict(np.load(os.path.join(d, f"rank{r}.npz"))) for r in range(2)]
+    grids = np.concatenate([ref_org.grid(v).ravel() for v in range(sc.n_views)])
+    for g in got:
+        for k in want:
+            assert np.array_equal(g[k], want[k]), k
+        assert np.array_equal(g["grids"], grids)
+    # the work really was split: both ranks produced records, none produced all of them
+    assert all(0 < int(g["local"]) < int(g["passed"]) for g in got)

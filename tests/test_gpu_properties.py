@@ -1,0 +1,105 @@
+"""Size-independent properties of the CUDA path at sizes the oracle cannot finish in
+seconds (BASELINE configs C2/C3 shapes, reduced image size)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sphere(orc):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from densepoints_b200 import build as b
+    b.build_cuda()
+    from densepoints_b200 import capi, scenes
+    sc = scenes.make_sphere_scene(seed=2, n_views=16, width=640, height=480, f=500.0)
+    seeds = scenes.make_seeds(sc, 200_000, seed=3)
+    ctx = capi.Context(0)
+    ctx.set_views(sc.P, sc.images)
+    yield sc, seeds, ctx
+    ctx.close()
+
+
+def test_c3_shape_scoring_properties(sphere, orc):
+    """C3 shape: many patches x 8 forced-visible views, mu = 7."""
+    from densepoints_b200 import scenes
+    sc, seeds, ctx = sphere
+    nvis, vis = scenes.force_visible(sc, seeds, 8)
+    ncc = ctx.score(seeds["pos"], seeds["nrm"], seeds["ref"], nvis, vis, 7)
+    assert ncc.shape == (200_000, 8)
+    assert (ncc[:, 0] == 0).all()
+    assert np.isfinite(ncc).all() and ncc.min() >= -1.0 - 1e-6 and ncc.max() <= 1.0 + 1e-6
+    # determinism: a second launch gives identical bits
+    assert np.array_equal(ncc, ctx.score(seeds["pos"], seeds["nrm"], seeds["ref"], nvis, vis, 7))
+    # batch-composition independence: any slice scores the same as in the full batch
+    sl = slice(77_777, 79_000)
+    part = ctx.score(seeds["pos"][sl], seeds["nrm"][sl], seeds["ref"][sl], nvis[sl], vis[sl], 7)
+    assert np.array_equal(part, ncc[sl])
+    # permutation of the non-anchor views permutes the scores (anchor = first entry)
+    perm = vis.copy()
+    perm[:, 1:] = perm[:, :0:-1]
+    ncc_p = ctx.score(seeds["pos"], seeds["nrm"], seeds["ref"], nvis, perm, 7)
+    assert np.array_equal(ncc_p[:, 1:], ncc[:, :0:-1])
+    # anchor duplicated as a second view scores exactly 1 (or -1 if its texture is empty)
+    dup = vis.copy()
+    dup[:, 1] = dup[:, 0]
+    ncc_d = ctx.score(seeds["pos"], seeds["nrm"], seeds["ref"], nvis, dup, 7)
+    ok = ncc_d[:, 1] != -1.0
+    assert ok.mean() > 0.9 and np.abs(ncc_d[ok, 1] - 1.0).max() < 1e-6
+    # spot check against the oracle on a random subsample
+    orc.set_homography_mode(1)
+    try:
+        V = orc.Views(sc.P, sc.images)
+        idx = np.random.default_rng(0).choice(200_000, 1500, replace=False)
+        o = orc.score_batch(V, seeds["pos"][idx], seeds["nrm"][idx], seeds["ref"][idx], nvis[idx],
+                            vis[idx], 7)
+        assert np.abs(o - ncc[idx]).max() < 1e-6
+    finally:
+        orc.set_homography_mode(0)
+
+
+def test_c2_shape_filter_refine_properties(sphere, orc):
+    sc, seeds, ctx = sphere
+    n = 100_000
+    pos, nrm, ref = seeds["pos"][:n], seeds["nrm"][:n], seeds["ref"][:n]
+    nvis, vis, _, _ = ctx.visibility(pos, nrm, ref)
+    keep, fnvis, fvis = ctx.filter(pos, nrm, ref, nvis, vis, 7)
+    assert 0.05 < keep.mean() < 0.95
+    # filtering only ever removes entries, keeps order, and the last entry always survives
+    assert (fnvis <= nvis).all()
+    m2 = nvis >= 2
+    last = vis[np.arange(n), np.maximum(nvis - 1, 0)]
+    flast = fvis[np.arange(n), np.maximum(fnvis - 1, 0)]
+    assert np.array_equal(last[m2], flast[m2])
+    for i in np.random.default_rng(1).choice(n, 500, replace=False):
+        a, b = list(vis[i, :nvis[i]]), list(fvis[i, :fnvis[i]])
+        it = iter(a)
+        assert all(x in it for x in b)                    # b is a subsequence of a
+    # idempotence of refinement bookkeeping: masked-out patches are untouched, evals == 0
+    p2, n2, ev, xb = ctx.refine(pos, nrm, ref, fnvis, fvis, 7, mask=keep)
+    out = keep == 0
+    assert np.array_equal(p2[out], pos[out]) and np.array_equal(n2[out], nrm[out])
+    assert (ev[out] == 0).all() and (ev[~out] >= 4).all() and ev.max() <= 503
+    # refinement never makes the objective worse than the start vertex set allows:
+    # mean NCC of the refined survivors goes up
+    k = np.arange(vis.shape[1])[None, :]
+    sm = (k >= 1) & (k < fnvis[:, None]) & (keep[:, None] == 1)
+    before = ctx.score(pos, nrm, ref, fnvis, fvis, 7)[sm].mean()
+    after = ctx.score(p2, n2, ref, fnvis, fvis, 7)[sm].mean()
+    assert after > before + 0.02
+    # a masked run equals an explicitly compacted run (Seed::RemovePatches) bit for bit
+    m = keep.astype(bool)
+    p3, n3, ev3, _ = ctx.refine(pos[m], nrm[m], ref[m], fnvis[m], fvis[m], 7)
+    assert np.array_equal(p3, p2[m]) and np.array_equal(n3, n2[m]) and np.array_equal(ev3, ev[m])
+    # spot check against the oracle
+    orc.set_homography_mode(1)
+    try:
+        V = orc.Views(sc.P, sc.images)
+        idx = np.where(m)[0][:300]
+        op, on, ofc, _ = orc.refine_batch(V, pos[idx], nrm[idx], ref[idx], fnvis[idx], fvis[idx], 7)
+        assert np.array_equal(ofc, ev[idx])
+        assert np.array_equal(op, p2[idx]) and np.array_equal(on, n2[idx])
+    finally:
+        orc.set_homography_mode(0)

@@ -48,6 +48,12 @@ def test_golden_gray(orc, golden_primitives):
     assert np.array_equal(mine, g["gray"])
 
 
+def test_golden_pyrdown(orc, golden_primitives):
+    g = golden_primitives
+    assert np.array_equal(orc.pyrdown(g["pyr_src"]), g["pyr_dst"])      # odd sizes, random noise
+    assert np.array_equal(orc.pyrdown(g["pyr_src2"]), g["pyr_dst2"])    # a rendered scene image
+
+
 def test_golden_textures_ncc_filter(orc, golden_scoring, golden_views):
     g = golden_scoring
     for s in (5, 7, 11, 16):
