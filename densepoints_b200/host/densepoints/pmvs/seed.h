@@ -1,0 +1,84 @@
+// densepoints/pmvs/seed.h -- the batched bodies of Seed::FilterPatches / OptimizePatches /
+// RemovePatches (reference methods/pmvs/seed.cpp:110-156) and of the patch-creation loop's
+// visibility step (seed.cpp:26-54): one C-ABI call per loop instead of one Optimization
+// object per patch.
+#ifndef DENSEPOINTS_B200_PMVS_SEED
+#define DENSEPOINTS_B200_PMVS_SEED
+
+#include <vector>
+
+#include "densepoints/pmvs/optimization.h"
+
+namespace DensePoints {
+namespace PMVS {
+
+class SeedCUDA {
+ public:
+  SeedCUDA(Session session, size_t cell_size = 16 /* MatcherOptions::cell_size, matcher.h:25 */,
+           double score_threshold = 0.6, size_t minimum_visible_image = 3)
+      : session_(session), cell_size_(cell_size), thr_(score_threshold), min_vis_(minimum_visible_image) {}
+
+  void SetPatches(const Patches &p) { patches_ = p; }
+  void GetPatches(Patches &p) const { p = patches_; }
+  Patches &patches() { return patches_; }
+
+  // Patch::InitRelatedImages for every patch (seed.cpp:47)
+  void InitRelatedImages() {
+    if (patches_.empty()) return;
+    std::vector<Patch *> ptr = Pointers(patches_);
+    PatchBatch b(ptr.data(), ptr.size(), (int)session_->views()->size());
+    std::vector<int32_t> ncand(ptr.size()), cand(ptr.size() * (size_t)b.soa.vstride, -1);
+    session_->Check(dp_visibility(session_->ctx(), &b.soa, ncand.data(), cand.data()), "dp_visibility");
+    b.StoreVisible(ptr.data());
+    for (size_t i = 0; i < ptr.size(); ++i) {
+      ImagesIndices c;
+      for (int k = 0; k < ncand[i] && k < b.soa.vstride; ++k) c.push_back((size_t)cand[i * b.soa.vstride + k]);
+      ptr[i]->SetPotentiallyVisibleImages(c);
+    }
+  }
+  void OptimizeAndRefinePatches() {  // seed.cpp:88-108
+    FilterPatches();
+    OptimizePatches();
+  }
+  void FilterPatches() {  // seed.cpp:110-126
+    if (patches_.empty()) return;
+    std::vector<Patch *> ptr = Pointers(patches_);
+    PatchBatch b(ptr.data(), ptr.size());
+    OptimizationCUDA::WithThresholds guard(*session_, thr_, min_vis_);
+    std::vector<uint8_t> keep(ptr.size());
+    session_->Check(dp_filter(session_->ctx(), &b.soa, (int)cell_size_, keep.data()), "dp_filter");
+    b.StoreVisible(ptr.data());
+    std::vector<size_t> to_remove;
+    for (size_t i = 0; i < keep.size(); ++i)
+      if (!keep[i]) to_remove.push_back(i);
+    RemovePatches(to_remove);
+  }
+  void OptimizePatches() {  // seed.cpp:128-144 (Optimize always returns true: nothing removed)
+    if (patches_.empty()) return;
+    std::vector<Patch *> ptr = Pointers(patches_);
+    PatchBatch b(ptr.data(), ptr.size());
+    evals_.assign(ptr.size(), 0);
+    session_->Check(dp_refine(session_->ctx(), &b.soa, (int)cell_size_, nullptr, evals_.data(), nullptr), "dp_refine");
+    b.StoreGeometry(ptr.data());
+  }
+  void RemovePatches(const std::vector<size_t> &patch_indices) {  // seed.cpp:146-156
+    size_t remove_offset = 0;
+    for (size_t index_to_remove : patch_indices) {
+      patches_.erase(patches_.begin() + (index_to_remove - remove_offset));
+      ++remove_offset;
+    }
+  }
+  const std::vector<int32_t> &LastEvals() const { return evals_; }
+
+ private:
+  Session session_;
+  size_t cell_size_;
+  double thr_;
+  size_t min_vis_;
+  Patches patches_;
+  std::vector<int32_t> evals_;
+};
+
+}  // namespace PMVS
+}  // namespace DensePoints
+#endif
