@@ -42,6 +42,16 @@ def b_alg(s, nv):
     return 3.0 * (2 * (s // 2) + 2) ** 2 + 4.0 + (28.0 + 2.0 * nv) / max(nv, 1)
 
 
+def ncu_refine_capture():
+    """dram bytes / instruction counts of the refine kernel on this workload, from the committed
+    ncu --set full capture (profiles/r01_refine_traffic.json); None if absent."""
+    p = os.path.join(ROOT, "profiles", "r01_refine_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -305,13 +315,26 @@ def main():
     alg_bytes = e_refine * b_alg(CELL, mean_nv)
     peak, peak_src = hbm_peak()
     achieved = alg_bytes / (refine_kernel_ms * 1e-3) / 1e9
+    cap = ncu_refine_capture() if not args.small and args.seeds == 1 << 20 else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "kernel": "dp_refine_kernel<2>",
+                "frac": achieved / peak,
+                "traffic": cap["dram_bytes_per_launch"] if cap else None,
+                "kernel": "dp_refine_kernel<2>",
                 "kernel_ms": refine_kernel_ms, "peak_source": peak_src,
-                "alg_bytes_per_eval": b_alg(CELL, mean_nv),
+                "alg_bytes_per_eval": b_alg(CELL, mean_nv), "alg_bytes_per_launch": alg_bytes,
                 "share_of_step": refine_kernel_ms * args.steps / gpu_ms,
-                "note": "issue-bound gather/reduce (~1.7k ops per eval): the image set (79 MB "
-                        "BGRx) is L2-resident, so HBM is not the binding roof"}
+                "note": "the binding roof is instruction issue, not HBM: one patch-view eval is "
+                        "~530 warp instructions (ncu), the 79 MB BGRx image set is L2-resident "
+                        "and DRAM traffic is <1% of the algorithmic bytes"}
+    if cap:
+        sm = 148
+        issue_peak = sm * 4 * (clocks["sm_mhz"] or 1965.0) * 1e6       # warp-inst/s
+        inst_per_eval = cap["warp_inst_per_launch"] / cap["evals_per_launch"]
+        roofline["issue"] = {"warp_inst_per_eval": inst_per_eval,
+                             "achieved_warp_inst_per_s": inst_per_eval * e_refine / (refine_kernel_ms * 1e-3),
+                             "peak_warp_inst_per_s": issue_peak,
+                             "frac": inst_per_eval * e_refine / (refine_kernel_ms * 1e-3) / issue_peak,
+                             "source": cap["source"]}
 
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------
     cpu = None

@@ -232,6 +232,24 @@ class Context:
         self._ck(lib().dp_color(self._h, C.byref(s)), "dp_color")
         return rgb
 
+    def create_patches(self, points, vstride=None):
+        """Seed::CreatePatchesFromPoints: points (n,3) float64 -> dict(pos,nrm,ref,nvis,vis)."""
+        points = np.ascontiguousarray(points, dtype=np.float64)
+        n = points.shape[0]
+        vs = vstride or self.num_views()
+        out = dict(pos=np.zeros((n, 3), np.float32), nrm=np.zeros((n, 3), np.float32),
+                   ref=np.zeros(n, np.int32), nvis=np.zeros(n, np.int32),
+                   vis=np.full((max(n, 1), vs), -1, np.int32)[:n])
+        s = DpPatchSoa()
+        s.n, s.vstride = n, vs
+        s.pos, s.nrm, s.ref, s.nvis, s.vis = (_ptr(out[k]) for k in ("pos", "nrm", "ref", "nvis", "vis"))
+        self._ck(lib().dp_create_patches(self._h, _ptr(points), C.c_int(n), C.byref(s), None, None),
+                 "dp_create_patches")
+        return out
+
+    def export_ply(self, path):
+        self._ck(lib().dp_export_ply(self._h, C.c_char_p(path.encode())), "dp_export_ply")
+
     # ---- organizer / expansion ---------------------------------------------------------------
     def organizer_reset(self):
         self._ck(lib().dp_organizer_reset(self._h), "dp_organizer_reset")

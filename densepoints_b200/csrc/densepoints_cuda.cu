@@ -386,12 +386,12 @@ template <int NPASS>
 static cudaError_t launch_refine(const DpRefineArgs &a, int sm_count, cudaStream_t st) {
   int per_sm = 1;
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dp_refine_kernel<NPASS>,
-                                                                DP_WARPS * 32, 0);
+                                                                DP_RWARPS * 32, 0);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
-  long long want = ((long long)a.p.n + DP_WARPS - 1) / DP_WARPS;
+  long long want = ((long long)a.p.n + DP_RWARPS - 1) / DP_RWARPS;
   long long grid = std::min<long long>(want, (long long)sm_count * per_sm);
-  dp_refine_kernel<NPASS><<<(unsigned)grid, DP_WARPS * 32, 0, st>>>(a);
+  dp_refine_kernel<NPASS><<<(unsigned)grid, DP_RWARPS * 32, 0, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -618,3 +618,4 @@ extern "C" int dp_color(dp_context *ctx, dp_patch_soa *h) {
 
 #include "dp_expand.cuh"
 #include "dp_pyramid.cuh"
+#include "dp_seed.cuh"

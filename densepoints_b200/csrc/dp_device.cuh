@@ -144,7 +144,7 @@ struct __align__(16) DpViewSetup {
   const uint32_t *src;  // first pixel of the ROI (packed BGRx)
   int pitch, rw, rh;    // image pitch (pixels), ROI width / height
   int ok;               // 0 where the reference pushes an empty cv::Mat
-  float inv_rw;         // 1 / rw for the staging loop
+  int lgp;              // log2 of the staged tile's row pitch (next power of two >= rw)
   int pad;
 };
 static_assert(sizeof(DpViewSetup) == 96, "DpViewSetup layout");
@@ -220,7 +220,7 @@ __device__ __forceinline__ void dp_setup_views(const DpViewDev *__restrict__ vie
       R.rw = rw;
       R.rh = rh;
       R.ok = ok ? 1 : 0;
-      R.inv_rw = __fdividef(1.0f, (float)max(rw, 1));
+      R.lgp = 32 - __clz(max(rw, 1) - 1);  // ceil(log2(rw))
     }
   }
 }
@@ -238,62 +238,67 @@ __device__ __forceinline__ void dp_view_texture(const DpViewSetup &R, int npx,
                M6 = R.M[6], M7 = R.M[7];
   const uint32_t *__restrict__ src = R.src;
   const int pitch = R.pitch, rw = R.rw, rh = R.rh;
-  // ---- stage the ROI into shared memory (flat index, row-coalesced 32-bit loads) ----------
-  const int area = rw * rh;
+  // ---- stage the ROI into shared memory: tile rows padded to a power-of-two pitch so the
+  // flat index splits with a shift and a mask; each 32-lane step loads 32/pitch whole rows
+  // with 32-bit loads (one 128-B line per row for ROIs up to 32 px wide).
+  const int lgp = R.lgp;
+  const int area = rh << lgp;
   const bool staged = area <= tile_cap;
   if (staged) {
-    const float inv_w = R.inv_rw;
+    const int cmask = (1 << lgp) - 1;
     for (int t = lane; t < area; t += 32) {
-      const int r = (int)(((float)t + 0.5f) * inv_w);
-      tile[t] = __ldg(src + (unsigned)(r * pitch + (t - r * rw)));
+      const int r = t >> lgp, c = t & cmask;
+      if (c < rw) tile[t] = __ldg(src + (unsigned)(r * pitch + c));
     }
     __syncwarp();
   }
   // ---- warp the texel grid ------------------------------------------------------------------
+  // Branch-free: lanes past the last texel compute on a clamped (harmless) coordinate and are
+  // masked at the end, so the NPASS independent passes can be interleaved by the scheduler.
 #pragma unroll
   for (int j = 0; j < NPASS; ++j) {
     const int i = lane + 32 * j;
-    g[j] = 0;
-    if (i < npx) {
-      double x, y;
-      tx.get(j, i, x, y);
-      const double Wd = fma(M6, x, fma(M7, y, 1.0));
-      double r = dp_rcp(Wd);
-      r = (Wd != 0.0) ? r : 0.0;  // W ? INTER_TAB_SIZE / W : 0
-      const double fX = fma(M0, x, fma(M1, y, M2)) * r;
-      const double fY = fma(M3, x, fma(M4, y, M5)) * r;
-      const int Xi = __double2int_rn(fX);  // saturate_cast<int>(cvRound), half to even
-      const int Yi = __double2int_rn(fY);
-      const int sx = Xi >> 5, axw = Xi & 31;  // INTER_BITS = 5
-      const int sy = Yi >> 5, ayw = Yi & 31;
-      const int x0 = min(max(sx, 0), rw - 1), x1 = min(max(sx + 1, 0), rw - 1);  // BORDER_REPLICATE
-      const int y0 = min(max(sy, 0), rh - 1), y1 = min(max(sy + 1, 0), rh - 1);  // at the ROI edge
-      uint32_t p00, p01, p10, p11;
-      if (staged) {
-        p00 = tile[y0 * rw + x0]; p01 = tile[y0 * rw + x1];
-        p10 = tile[y1 * rw + x0]; p11 = tile[y1 * rw + x1];
-      } else {
-        const uint32_t *r0 = src + (size_t)y0 * pitch, *r1 = src + (size_t)y1 * pitch;
-        p00 = __ldg(r0 + x0); p01 = __ldg(r0 + x1);
-        p10 = __ldg(r1 + x0); p11 = __ldg(r1 + x1);
-      }
-      // separable form of the 15-bit weights (32-ax)(32-ay)*32 ...: exact in integers,
-      // (sum*32 + 2^14) >> 15 == (sum + 2^9) >> 10.
-      const uint32_t wx1 = (uint32_t)axw, wx0 = 32u - wx1, wy1 = (uint32_t)ayw, wy0 = 32u - wy1;
-      const uint32_t br0 = (p00 & 0x00ff00ffu) * wx0 + (p01 & 0x00ff00ffu) * wx1;  // B | R<<16
-      const uint32_t br1 = (p10 & 0x00ff00ffu) * wx0 + (p11 & 0x00ff00ffu) * wx1;
-      const uint32_t g0 = ((p00 >> 8) & 0xffu) * wx0 + ((p01 >> 8) & 0xffu) * wx1;
-      const uint32_t g1 = ((p10 >> 8) & 0xffu) * wx0 + ((p11 >> 8) & 0xffu) * wx1;
-      const uint32_t B = ((br0 & 0xffffu) * wy0 + (br1 & 0xffffu) * wy1 + 512u) >> 10;
-      const uint32_t Rr = ((br0 >> 16) * wy0 + (br1 >> 16) * wy1 + 512u) >> 10;
-      const uint32_t G = (g0 * wy0 + g1 * wy1 + 512u) >> 10;
-      // cv::cvtColor(BGR2GRAY), 8U: 15-bit fixed point
-      g[j] = (int)((3735u * B + 19235u * G + 9798u * Rr + (1u << 14)) >> 15);
-      if (WRITE_TEX) {
-        tex_out[3 * i + 0] = (uint8_t)B;
-        tex_out[3 * i + 1] = (uint8_t)G;
-        tex_out[3 * i + 2] = (uint8_t)Rr;
-      }
+    double x, y;
+    tx.get(j, i, x, y);
+    const double Wd = fma(M6, x, fma(M7, y, 1.0));
+    double r = dp_rcp(Wd);
+    r = (Wd != 0.0) ? r : 0.0;  // W ? INTER_TAB_SIZE / W : 0
+    const double fX = fma(M0, x, fma(M1, y, M2)) * r;
+    const double fY = fma(M3, x, fma(M4, y, M5)) * r;
+    const int Xi = __double2int_rn(fX);  // saturate_cast<int>(cvRound), half to even
+    const int Yi = __double2int_rn(fY);
+    const int sx = Xi >> 5, axw = Xi & 31;  // INTER_BITS = 5
+    const int sy = Yi >> 5, ayw = Yi & 31;
+    const int x0 = min(max(sx, 0), rw - 1), x1 = min(max(sx + 1, 0), rw - 1);  // BORDER_REPLICATE
+    const int y0 = min(max(sy, 0), rh - 1), y1 = min(max(sy + 1, 0), rh - 1);  // at the ROI edge
+    uint32_t p00, p01, p10, p11;
+    if (staged) {
+      const int o0 = y0 << lgp, o1 = y1 << lgp;
+      p00 = tile[o0 + x0]; p01 = tile[o0 + x1];
+      p10 = tile[o1 + x0]; p11 = tile[o1 + x1];
+    } else {
+      const uint32_t *r0 = src + (size_t)y0 * pitch, *r1 = src + (size_t)y1 * pitch;
+      p00 = __ldg(r0 + x0); p01 = __ldg(r0 + x1);
+      p10 = __ldg(r1 + x0); p11 = __ldg(r1 + x1);
+    }
+    // separable form of the 15-bit weights (32-ax)(32-ay)*32 ...: exact in integers,
+    // (sum*32 + 2^14) >> 15 == (sum + 2^9) >> 10.  B and R share one multiply per tap pair
+    // (B | R<<16, each partial sum <= 255*32).
+    const uint32_t wx1 = (uint32_t)axw, wx0 = 32u - wx1, wy1 = (uint32_t)ayw, wy0 = 32u - wy1;
+    const uint32_t br0 = (p00 & 0x00ff00ffu) * wx0 + (p01 & 0x00ff00ffu) * wx1;  // B | R<<16
+    const uint32_t br1 = (p10 & 0x00ff00ffu) * wx0 + (p11 & 0x00ff00ffu) * wx1;
+    const uint32_t g0 = ((p00 >> 8) & 0xffu) * wx0 + ((p01 >> 8) & 0xffu) * wx1;
+    const uint32_t g1 = ((p10 >> 8) & 0xffu) * wx0 + ((p11 >> 8) & 0xffu) * wx1;
+    const uint32_t B = ((br0 & 0xffffu) * wy0 + (br1 & 0xffffu) * wy1 + 512u) >> 10;
+    const uint32_t Rr = ((br0 >> 16) * wy0 + (br1 >> 16) * wy1 + 512u) >> 10;
+    const uint32_t G = (g0 * wy0 + g1 * wy1 + 512u) >> 10;
+    // cv::cvtColor(BGR2GRAY), 8U: 15-bit fixed point
+    const int gray = (int)((3735u * B + 19235u * G + 9798u * Rr + (1u << 14)) >> 15);
+    g[j] = (i < npx) ? gray : 0;
+    if (WRITE_TEX && i < npx) {
+      tex_out[3 * i + 0] = (uint8_t)B;
+      tex_out[3 * i + 1] = (uint8_t)G;
+      tex_out[3 * i + 2] = (uint8_t)Rr;
     }
   }
   if (staged) __syncwarp();  // the tile may be overwritten by the next view

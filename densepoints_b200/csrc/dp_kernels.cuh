@@ -17,7 +17,13 @@
 __host__ __device__ constexpr int dp_score_min_ctas(int npass) {
   return npass <= 2 ? 4 : (npass <= 4 ? 3 : (npass <= 8 ? 2 : 1));
 }
-__host__ __device__ constexpr int dp_refine_min_ctas(int npass) { return npass <= 8 ? 2 : 1; }
+#ifndef DP_RWARPS
+#define DP_RWARPS 8  // warps per CTA of the refine kernel
+#endif
+#ifndef DP_RMINCTA
+#define DP_RMINCTA 2
+#endif
+__host__ __device__ constexpr int dp_refine_min_ctas(int npass) { return npass <= 8 ? DP_RMINCTA : 1; }
 
 struct DpPatchArgs {
   const DpViewDev *views;
@@ -196,9 +202,12 @@ __device__ __forceinline__ void dp_unparametrize(const double *__restrict__ C, c
   const double k = xadd(1.0, depth);
 #pragma unroll
   for (int j = 0; j < 3; ++j) p[j] = xadd(C[j], xmul(k, xsub(p0[j], C[j])));
-  double sa, ca, sb, cb;
-  sincos(roll, &sa, &ca);
-  sincos(pitch, &sb, &cb);
+  // one sincos instruction stream serves both angles: even lanes take roll, odd lanes pitch
+  const int lane = threadIdx.x & 31;
+  double sv, cv;
+  sincos((lane & 1) ? pitch : roll, &sv, &cv);
+  const double sa = __shfl_sync(DP_FULL, sv, 0), ca = __shfl_sync(DP_FULL, cv, 0);
+  const double sb = __shfl_sync(DP_FULL, sv, 1), cb = __shfl_sync(DP_FULL, cv, 1);
   // rotation rows: [cb 0 -sb; sa*sb ca cb*sa; ca*sb -sa ca*cb]
   n[0] = xadd(xmul(cb, n0[0]), xmul(-sb, n0[2]));
   n[1] = xadd(xadd(xmul(xmul(sa, sb), n0[0]), xmul(ca, n0[1])), xmul(xmul(cb, sa), n0[2]));
@@ -270,9 +279,9 @@ __device__ __forceinline__ void dp_shrink_vertex(DpSlots &S, int lane, int idx, 
 }
 
 template <int NPASS>
-__global__ void __launch_bounds__(DP_WARPS * 32, dp_refine_min_ctas(NPASS)) dp_refine_kernel(DpRefineArgs a) {
-  __shared__ uint32_t tiles[DP_WARPS][DpTileCfg<NPASS>::kTilePx];
-  __shared__ DpViewSetup recs[DP_WARPS][DP_ROUND];
+__global__ void __launch_bounds__(DP_RWARPS * 32, dp_refine_min_ctas(NPASS)) dp_refine_kernel(DpRefineArgs a) {
+  __shared__ uint32_t tiles[DP_RWARPS][DpTileCfg<NPASS>::kTilePx];
+  __shared__ DpViewSetup recs[DP_RWARPS][DP_ROUND];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = a.p.s, npx = s * s;
   DpTexels<NPASS> tx;

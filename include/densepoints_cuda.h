@@ -182,6 +182,18 @@ int dp_visibility_dev(dp_context *ctx, dp_patch_dev *p, int32_t *ncand, int32_t 
                       void *stream);
 int dp_color_dev(dp_context *ctx, dp_patch_dev *p, void *stream);
 
+/* ---- the steps either side of the path -----------------------------------
+ * dp_create_patches: Seed::CreatePatchesFromPoints (seed.cpp:26-54) for n triangulated
+ * points (fp64, n*3): reference image = nearest camera centre (first minimum wins),
+ * normal = unit viewing ray, position/normal stored as fp32, then InitRelatedImages.
+ * `out` must have capacity n (out->n >= n on entry) and its vstride set; patch order = point
+ * order.  ncand/cand (optional) as in dp_visibility.
+ * dp_export_ply: the organizer's patch store as an ASCII PLY in the layout of the
+ * reference's PMVS::PrintCloud (utils.cpp:9-50): x y z, red green blue, nx ny nz. */
+int dp_create_patches(dp_context *ctx, const double *points, int n, dp_patch_soa *out,
+                      int32_t *ncand, int32_t *cand);
+int dp_export_ply(dp_context *ctx, const char *path);
+
 /* ---- image pyramid (new; the reference's modules/image is an empty placeholder,
  * modules/image/Image.h:1-7).  Level l of view v = cv::pyrDown applied l times, with
  * P_l = diag(2^-l, 2^-l, 1) P.  dp_build_pyramid creates levels 1..n_levels-1 on the

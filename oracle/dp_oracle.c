@@ -827,6 +827,41 @@ void orc_compute_color(const orc_view *views, int n_views, const float pos[3], u
   rgb[2] = (uint8_t)(sum[0] / count); /* b */
 }
 
+/* Seed::CreatePatchesFromPoints (seed.cpp:26-54), patches in point order. */
+void orc_create_patches(const orc_view *views, int n_views, int n, const double *points,
+                        double t_vis, double t_cand, float *pos, float *nrm, int *ref, int *nvis,
+                        int *vis, int vstride) {
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; ++i) {
+    const double *pt = points + 3 * i;
+    double d0[3] = {pt[0] - views[0].center[0], pt[1] - views[0].center[1], pt[2] - views[0].center[2]};
+    double min_distance = norm3(d0);
+    int min_index = 0;
+    for (int c = 1; c < n_views; ++c) {
+      double d[3] = {pt[0] - views[c].center[0], pt[1] - views[c].center[1], pt[2] - views[c].center[2]};
+      double distance = norm3(d);
+      if (distance < min_distance) {
+        min_index = c;
+        min_distance = distance;
+      }
+    }
+    double ptc[3] = {pt[0] - views[min_index].center[0], pt[1] - views[min_index].center[1],
+                     pt[2] - views[min_index].center[2]};
+    double nn = norm3(ptc);
+    for (int j = 0; j < 3; ++j) {
+      pos[3 * i + j] = (float)pt[j];
+      nrm[3 * i + j] = (float)(ptc[j] / nn);
+    }
+    ref[i] = min_index;
+    int *vi = vis + (size_t)i * vstride;
+    for (int k = 0; k < vstride; ++k) vi[k] = -1;
+    int nv, nc;
+    orc_init_related_images(views, n_views, min_index, nrm + 3 * i, pos + 3 * i, t_vis, t_cand, vi,
+                            &nv, NULL, &nc);
+    nvis[i] = nv;
+  }
+}
+
 /* ------------------------------------------------------------------------ */
 /* batched drivers (Seed::FilterPatches / OptimizePatches, seed.cpp:110-144)  */
 

@@ -157,6 +157,11 @@ void orc_visibility_batch(const orc_view *views, int n_views, int n, const float
                           const float *nrm, const int *ref, double t_vis, double t_cand, int *nvis,
                           int *vis, int *ncand, int *cand, int vstride);
 
+/* Seed::CreatePatchesFromPoints (seed.cpp:26-54); patches in point order. */
+void orc_create_patches(const orc_view *views, int n_views, int n, const double *points,
+                        double t_vis, double t_cand, float *pos, float *nrm, int *ref, int *nvis,
+                        int *vis, int vstride);
+
 /* ---- PatchOrganizer + Expand (patch_organizer.cpp, expand.cpp), 1-thread FIFO ---- */
 typedef struct orc_organizer orc_organizer;
 orc_organizer *orc_organizer_create(const orc_view *views, int n_views, const orc_params *prm);

@@ -256,6 +256,18 @@ def visibility_batch(views: Views, pos, nrm, ref, t_vis=0.78, t_cand=1.04, vstri
     return nvis, vis, ncand, cand
 
 
+def create_patches(views: Views, points, t_vis=0.78, t_cand=1.04):
+    points = np.ascontiguousarray(points, dtype=np.float64)
+    n = points.shape[0]
+    out = dict(pos=np.zeros((n, 3), np.float32), nrm=np.zeros((n, 3), np.float32),
+               ref=np.zeros(n, np.int32), nvis=np.zeros(n, np.int32),
+               vis=np.full((n, views.n), -1, np.int32))
+    lib().orc_create_patches(views.arr, C.c_int(views.n), C.c_int(n), _p(points), C.c_double(t_vis),
+                             C.c_double(t_cand), _p(out["pos"]), _p(out["nrm"]), _p(out["ref"]),
+                             _p(out["nvis"]), _p(out["vis"]), C.c_int(views.n))
+    return out
+
+
 def compute_color(views: Views, pos):
     pos = _f32(pos)
     out = np.zeros((pos.shape[0], 3), np.uint8)

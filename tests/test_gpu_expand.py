@@ -149,3 +149,37 @@ def test_scoring_on_pyramid_level(capi_mod, exact_orc):
         assert np.array_equal(valid, o_valid) and np.array_equal(tex, o_tex)
         assert np.abs(ncc - o_ncc).max() < 1e-6
     ctx.close()
+
+
+def test_create_patches_and_ply_export(capi_mod, exact_orc, tmp_path):
+    """SURVEY 8f: Seed::CreatePatchesFromPoints on the device; PLY export of the store."""
+    from densepoints_b200 import scenes
+    sc = scenes.make_sphere_scene(seed=2, n_views=16, width=320, height=240, f=250.0)
+    rng = np.random.default_rng(3)
+    d = rng.normal(size=(5000, 3))
+    pts = d / np.linalg.norm(d, axis=1, keepdims=True) * sc.radius * rng.uniform(0.97, 1.03, (5000, 1))
+    ctx = capi_mod.Context(0)
+    ctx.set_views(sc.P, sc.images)
+    V = exact_orc.Views(sc.P, sc.images)
+    got = ctx.create_patches(pts)
+    want = exact_orc.create_patches(V, pts)
+    for k in ("ref", "nvis", "vis", "pos", "nrm"):
+        assert np.array_equal(got[k], want[k]), k
+    assert len(set(got["ref"])) > 4 and got["nvis"].max() >= 3
+    # store -> PLY in the reference's PrintCloud layout
+    ctx.organizer_reset()
+    acc = ctx.organizer_insert(got["pos"], got["nrm"], got["ref"], got["nvis"], got["vis"])
+    path = str(tmp_path / "cloud.ply")
+    ctx.export_ply(path)
+    lines = open(path).read().split("\n")
+    st = ctx.organizer_export()
+    assert lines[0] == "ply" and lines[1] == "format ascii 1.0"
+    assert lines[2] == f"element vertex {acc.sum()}" and lines[12] == "end_header"
+    assert lines[3:12] == ["property float x", "property float y", "property float z",
+                           "property uchar red", "property uchar green", "property uchar blue",
+                           "property float nx", "property float ny", "property float nz"]
+    rows = np.array([[float(t) for t in ln.split()] for ln in lines[13:13 + acc.sum()]])
+    assert rows.shape == (acc.sum(), 9)
+    assert np.allclose(rows[:, :3], st["pos"], rtol=1e-5) and np.allclose(rows[:, 6:], st["nrm"], rtol=1e-5, atol=1e-7)
+    assert np.array_equal(rows[:, 3:6].astype(np.uint8), st["rgb"])
+    ctx.close()
