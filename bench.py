@@ -165,7 +165,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--seeds", type=int, default=1 << 20)
-    ap.add_argument("--cpu-sample", type=int, default=3072)
+    ap.add_argument("--cpu-sample", type=int, default=16384)
     ap.add_argument("--small", action="store_true", help="reduced scene/seed count (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -104,7 +104,7 @@ extern "C" void dp_destroy(dp_context *ctx) {
   DpDevBuf *bufs[] = {&ctx->d_views, &ctx->s_pos, &ctx->s_nrm, &ctx->s_ref, &ctx->s_nvis,
                       &ctx->s_vis, &ctx->s_rgb, &ctx->s_ncc, &ctx->s_tex, &ctx->s_valid,
                       &ctx->s_keep, &ctx->s_evals, &ctx->s_xbest, &ctx->s_cand, &ctx->s_ncand,
-                      &ctx->s_img, &ctx->s_misc, &ctx->work_counter, &ctx->e_pos, &ctx->e_nrm,
+                      &ctx->s_img, &ctx->s_misc, &ctx->work_counter, &ctx->s_order, &ctx->e_pos, &ctx->e_nrm,
                       &ctx->e_ref, &ctx->e_nvis, &ctx->e_vis, &ctx->e_keep, &ctx->e_seq,
                       &ctx->e_cells, &ctx->e_flags, &ctx->e_scan, &ctx->e_count, &ctx->org.grid,
                       &ctx->org.claim, &ctx->org.pos, &ctx->org.nrm, &ctx->org.rgb, &ctx->org.ref,
@@ -414,6 +414,19 @@ extern "C" int dp_refine_dev(dp_context *ctx, dp_patch_dev *p, int cell_size, co
   a.eps = ctx->prm.nm_eps;
   a.work_counter = ctx->work_counter.as<unsigned int>();
   a.mask = mask;
+  a.order = nullptr;
+  if (p->n >= 4096) {  // longest-first schedule (pays off once there are many waves of patches)
+    DP_CUDA(ctx, ctx->s_order.ensure((size_t)p->n * 4 + DP_ORDER_BINS * 4));
+    int32_t *order = ctx->s_order.as<int32_t>();
+    unsigned int *hist = reinterpret_cast<unsigned int *>(order + p->n);
+    DP_CUDA(ctx, cudaMemsetAsync(hist, 0, DP_ORDER_BINS * 4, st));
+    const unsigned blocks = (unsigned)((p->n + 255) / 256);
+    dp_order_hist_kernel<<<blocks, 256, 0, st>>>(p->nvis, mask, p->n, hist);
+    dp_order_scan_kernel<<<1, 1, 0, st>>>(hist);
+    dp_order_scatter_kernel<<<blocks, 256, 0, st>>>(p->nvis, mask, p->n, hist, order);
+    ctx->launches += 3;
+    a.order = order;
+  }
   cudaError_t e;
   switch (npass_for(cell_size)) {
     case 1: e = launch_refine<1>(a, ctx->sm_count, st); break;

@@ -73,7 +73,7 @@ struct dp_context {
   // scratch for the host-buffer API
   DpDevBuf s_pos, s_nrm, s_ref, s_nvis, s_vis, s_rgb, s_ncc, s_tex, s_valid, s_keep, s_evals,
       s_xbest, s_cand, s_ncand, s_img, s_misc;
-  DpDevBuf work_counter;
+  DpDevBuf work_counter, s_order;
   // expansion scratch
   DpDevBuf e_pos, e_nrm, e_ref, e_nvis, e_vis, e_keep, e_seq, e_cells, e_flags, e_scan, e_count;
   DpOrganizer org;

@@ -193,7 +193,37 @@ struct DpRefineArgs {
   double eps;
   unsigned int *work_counter;  // zeroed before launch
   const uint8_t *mask;         // optional: refine only patches with mask[i] != 0
+  const int32_t *order;        // optional: work item k = patch order[k] (longest-first schedule)
 };
+
+// Longest-processing-time-first schedule for the persistent refine warps: the cost of a
+// patch is (evaluations x visible views); the view count is known up front, so patches are
+// handed out in descending view count (counting sort, 3 tiny kernels).  Results do not
+// depend on the order in which patches are processed.
+#define DP_ORDER_BINS 257
+__global__ void dp_order_hist_kernel(const int32_t *__restrict__ nvis, const uint8_t *__restrict__ mask,
+                                     int n, unsigned int *__restrict__ hist) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int key = (mask && mask[i] == 0) ? 0 : min(max(nvis[i], 0), DP_ORDER_BINS - 1);
+  atomicAdd(hist + (DP_ORDER_BINS - 1 - key), 1u);  // bin 0 = most views
+}
+__global__ void dp_order_scan_kernel(unsigned int *hist) {  // exclusive scan in place, 1 thread
+  unsigned int run = 0;
+  for (int b = 0; b < DP_ORDER_BINS; ++b) {
+    const unsigned int c = hist[b];
+    hist[b] = run;
+    run += c;
+  }
+}
+__global__ void dp_order_scatter_kernel(const int32_t *__restrict__ nvis, const uint8_t *__restrict__ mask,
+                                        int n, unsigned int *__restrict__ cursor,
+                                        int32_t *__restrict__ order) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int key = (mask && mask[i] == 0) ? 0 : min(max(nvis[i], 0), DP_ORDER_BINS - 1);
+  order[atomicAdd(cursor + (DP_ORDER_BINS - 1 - key), 1u)] = i;
+}
 
 // Optimization::UnparametrizePatch (optimization.cpp:78-96)
 __device__ __forceinline__ void dp_unparametrize(const double *__restrict__ C, const double n0[3],
@@ -293,7 +323,7 @@ __global__ void __launch_bounds__(DP_RWARPS * 32, dp_refine_min_ctas(NPASS)) dp_
     if (lane == 0) iu = atomicAdd(a.work_counter, 1u);
     iu = __shfl_sync(DP_FULL, iu, 0);
     if (iu >= (unsigned int)a.p.n) break;
-    const long long i = iu;
+    const long long i = a.order ? (long long)a.order[iu] : (long long)iu;
     if (a.mask != nullptr && a.mask[i] == 0) {  // removed by Seed::RemovePatches (seed.cpp:146-156)
       if (a.evals && lane == 0) a.evals[i] = 0;
       continue;
