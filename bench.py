@@ -282,13 +282,20 @@ def main():
                                 vis_h0)]
     h_pos, h_nrm, h_ref, h_nvis, h_vis = (h[1] for h in hold)
 
+    w = [pinned(np.empty_like(x)) for x in (h_pos, h_nrm, h_nvis, h_vis)]
+    w_pos, w_nrm, w_nvis, w_vis = (x[1] for x in w)
+    k_t, k_h = pinned(np.zeros(n, np.uint8))
+    e_t, e_h = pinned(np.zeros(n, np.int32))
+
     def step_e2e():
-        # what methods/pmvs would do through the drop-in: FilterPatches -> RemovePatches ->
-        # OptimizePatches, every call moving its host arrays in and its results out
-        k, fnvis, fvis = ctx.filter(h_pos, h_nrm, h_ref, h_nvis, h_vis, CELL)
-        m = k.astype(bool)
-        p2, n2, ev2, _ = ctx.refine(h_pos[m], h_nrm[m], h_ref[m], fnvis[m], fvis[m], CELL)
-        return int(h_nvis.sum()) + int((ev2.astype(np.int64) * fnvis[m]).sum()), int(m.sum())
+        # what methods/pmvs does through the drop-in: Seed::OptimizeAndRefinePatches =
+        # dp_filter_refine on the caller's (pinned) host arrays; one H2D of the patches, one
+        # D2H of keep / visible sets / refined geometry / evaluation counts.
+        np.copyto(w_pos, h_pos); np.copyto(w_nrm, h_nrm)
+        np.copyto(w_nvis, h_nvis); np.copyto(w_vis, h_vis)
+        ctx.filter_refine_inplace(w_pos, w_nrm, h_ref, w_nvis, w_vis, CELL, k_h, e_h)
+        m = k_h.astype(bool)
+        return int(h_nvis.sum()) + int((e_h[m].astype(np.int64) * w_nvis[m]).sum()), int(m.sum())
 
     e2e_steps = max(1, min(args.steps, 2))
     step_e2e()
@@ -306,8 +313,8 @@ def main():
         dist.all_reduce(e2e_ev, op=dist.ReduceOp.SUM)
     e2e_value = float(e2e_ev.item()) / float(e2e_dt.item())
     n_keep = int(keep.sum().item())
-    h2d = n * (12 + 12 + 4 + 4 + 4 * V) + n_keep * (12 + 12 + 4 + 4 + 4 * V)
-    d2h = n * (1 + 4 + 4 * V) + n_keep * (12 + 12 + 4 + 24)
+    h2d = n * (12 + 12 + 4 + 4 + 4 * V)
+    d2h = n * (1 + 4 + 4 * V + 12 + 12 + 4)
 
     # ---- roofline of the dominant kernel (refine) ------------------------------------------------
     mean_nv = float((nvis.to(torch.float64) * keep).sum().item() / max(n_keep, 1))

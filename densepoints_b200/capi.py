@@ -211,6 +211,24 @@ class Context:
                                  _ptr(xbest)), "dp_refine")
         return pos, nrm, evals, xbest
 
+    def filter_refine(self, pos, nrm, ref, nvis, vis, cell_size):
+        """Seed::OptimizeAndRefinePatches in one call (copies its inputs)."""
+        pos = np.array(pos, dtype=np.float32, copy=True, order="C")
+        nrm = np.array(nrm, dtype=np.float32, copy=True, order="C")
+        ref = np.ascontiguousarray(ref, dtype=np.int32)
+        nvis = np.array(nvis, dtype=np.int32, copy=True)
+        vis = np.array(vis, dtype=np.int32, copy=True, order="C")
+        keep = np.zeros(vis.shape[0], np.uint8)
+        evals = np.zeros(vis.shape[0], np.int32)
+        self.filter_refine_inplace(pos, nrm, ref, nvis, vis, cell_size, keep, evals)
+        return keep, nvis, vis, pos, nrm, evals
+
+    def filter_refine_inplace(self, pos, nrm, ref, nvis, vis, cell_size, keep, evals=None):
+        """dp_filter_refine on the caller's own (e.g. pinned) arrays, edited in place."""
+        s = _soa(pos, nrm, ref, nvis, vis)
+        self._ck(lib().dp_filter_refine(self._h, C.byref(s), C.c_int(cell_size), _ptr(keep),
+                                        _ptr(evals)), "dp_filter_refine")
+
     def visibility(self, pos, nrm, ref, vstride=None):
         pos, nrm = (np.ascontiguousarray(a, dtype=np.float32) for a in (pos, nrm))
         ref = np.ascontiguousarray(ref, dtype=np.int32)

@@ -584,6 +584,32 @@ extern "C" int dp_refine(dp_context *ctx, dp_patch_soa *h, int cell_size, const 
   return DP_OK;
 }
 
+extern "C" int dp_filter_refine(dp_context *ctx, dp_patch_soa *h, int cell_size, uint8_t *keep,
+                                int32_t *evals) {
+  if (!ctx) return DP_ERR_INVALID_ARG;
+  if (!keep) return dp_fail(ctx, DP_ERR_INVALID_ARG, "keep is null");
+  dp_patch_dev d;
+  int rc = upload_patches(ctx, h, &d, true);
+  if (rc != DP_OK) return rc;
+  if (h->n == 0) return DP_OK;
+  const size_t n = (size_t)h->n, vs = (size_t)h->vstride;
+  DP_CUDA(ctx, ctx->s_keep.ensure(n));
+  if (evals) DP_CUDA(ctx, ctx->s_evals.ensure(n * 4));
+  cudaStream_t st = ctx->stream;
+  if ((rc = dp_filter_dev(ctx, &d, cell_size, ctx->s_keep.as<uint8_t>(), st)) != DP_OK) return rc;
+  if ((rc = dp_refine_dev(ctx, &d, cell_size, ctx->s_keep.as<uint8_t>(),
+                          evals ? ctx->s_evals.as<int32_t>() : nullptr, nullptr, st)) != DP_OK)
+    return rc;
+  DP_CUDA(ctx, cudaMemcpyAsync(keep, ctx->s_keep.ptr, n, cudaMemcpyDeviceToHost, st));
+  DP_CUDA(ctx, cudaMemcpyAsync(h->nvis, d.nvis, n * 4, cudaMemcpyDeviceToHost, st));
+  DP_CUDA(ctx, cudaMemcpyAsync(h->vis, d.vis, n * vs * 4, cudaMemcpyDeviceToHost, st));
+  DP_CUDA(ctx, cudaMemcpyAsync(h->pos, d.pos, n * 12, cudaMemcpyDeviceToHost, st));
+  DP_CUDA(ctx, cudaMemcpyAsync(h->nrm, d.nrm, n * 12, cudaMemcpyDeviceToHost, st));
+  if (evals) DP_CUDA(ctx, cudaMemcpyAsync(evals, ctx->s_evals.ptr, n * 4, cudaMemcpyDeviceToHost, st));
+  DP_CUDA(ctx, cudaStreamSynchronize(st));
+  return DP_OK;
+}
+
 extern "C" int dp_visibility(dp_context *ctx, dp_patch_soa *h, int32_t *ncand, int32_t *cand) {
   if (!ctx) return DP_ERR_INVALID_ARG;
   dp_patch_dev d;

@@ -36,9 +36,21 @@ class SeedCUDA {
       ptr[i]->SetPotentiallyVisibleImages(c);
     }
   }
-  void OptimizeAndRefinePatches() {  // seed.cpp:88-108
-    FilterPatches();
-    OptimizePatches();
+  void OptimizeAndRefinePatches() {  // seed.cpp:88-108: FilterPatches(); OptimizePatches();
+    if (patches_.empty()) return;     // one upload / download for both stages
+    std::vector<Patch *> ptr = Pointers(patches_);
+    PatchBatch b(ptr.data(), ptr.size());
+    OptimizationCUDA::WithThresholds guard(*session_, thr_, min_vis_);
+    std::vector<uint8_t> keep(ptr.size());
+    evals_.assign(ptr.size(), 0);
+    session_->Check(dp_filter_refine(session_->ctx(), &b.soa, (int)cell_size_, keep.data(), evals_.data()),
+                    "dp_filter_refine");
+    b.StoreVisible(ptr.data());
+    b.StoreGeometry(ptr.data());
+    std::vector<size_t> to_remove;
+    for (size_t i = 0; i < keep.size(); ++i)
+      if (!keep[i]) to_remove.push_back(i);
+    RemovePatches(to_remove);
   }
   void FilterPatches() {  // seed.cpp:110-126
     if (patches_.empty()) return;

@@ -120,6 +120,14 @@ int dp_filter(dp_context *ctx, dp_patch_soa *patches, int cell_size, uint8_t *ke
 int dp_refine(dp_context *ctx, dp_patch_soa *patches, int cell_size, const uint8_t *mask,
               int32_t *evals, double *xbest);
 
+/* ---- Seed::OptimizeAndRefinePatches (seed.cpp:88-108) in one call: FilterPatches, then
+ * OptimizePatches on the survivors, with a single upload and a single download.
+ * On return nvis/vis are filtered as by dp_filter, keep[i] says whether patch i survived
+ * (the caller erases the others, Seed::RemovePatches), pos/nrm of the survivors are refined
+ * as by dp_refine (the others are unchanged), evals (optional) as in dp_refine. */
+int dp_filter_refine(dp_context *ctx, dp_patch_soa *patches, int cell_size, uint8_t *keep,
+                     int32_t *evals);
+
 /* ---- visibility: Patch::InitRelatedImages (patch.cpp:19-49) for every patch.
  * Writes nvis/vis of `patches` (visible) and, if non-NULL, ncand/cand
  * (potentially visible; cand is n*vstride). */

@@ -187,3 +187,17 @@ def test_edge_cases(capi_mod, c1):
         ctx.score(sd["pos"][:1], sd["nrm"][:1], sd["ref"][:1], c1["nvis"][:1], c1["vis"][:1], 1)
     with pytest.raises(capi_mod.DpError):
         ctx.score(sd["pos"][:1], sd["nrm"][:1], sd["ref"][:1], c1["nvis"][:1], c1["vis"][:1], 33)
+
+
+def test_filter_refine_fused_equals_two_calls(c1):
+    """dp_filter_refine == dp_filter then dp_refine on the survivors (seed.cpp:88-108)."""
+    d = c1
+    sd = d["seeds"]
+    keep, nvis, vis, pos, nrm, evals = d["ctx"].filter_refine(sd["pos"], sd["nrm"], sd["ref"],
+                                                            d["nvis"], d["vis"], 5)
+    k2, nv2, vis2 = d["ctx"].filter(sd["pos"], sd["nrm"], sd["ref"], d["nvis"], d["vis"], 5)
+    m = k2.astype(bool)
+    p2, n2, e2, _ = d["ctx"].refine(sd["pos"][m], sd["nrm"][m], sd["ref"][m], nv2[m], vis2[m], 5)
+    assert np.array_equal(keep, k2) and np.array_equal(nvis, nv2) and np.array_equal(vis, vis2)
+    assert np.array_equal(pos[m], p2) and np.array_equal(nrm[m], n2) and np.array_equal(evals[m], e2)
+    assert np.array_equal(pos[~m], sd["pos"][~m]) and (evals[~m] == 0).all()
