@@ -112,6 +112,7 @@ def run_reference(args):
         return
     from oracle import oracle as orc
     orc.build()
+    orc.use_all_cores()
     orc.set_homography_mode(0)           # the OpenCV procedure (findHomography's eigen-solve)
     sample = args.cpu_sample
     sc, seeds = make_workload(sample, small=args.small)
@@ -348,6 +349,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
         orc.build()
+        orc.use_all_cores()
         orc.set_homography_mode(0)
         ns = min(args.cpu_sample, n)
         OV = orc.Views(sc.P, sc.images)

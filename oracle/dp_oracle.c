@@ -25,6 +25,14 @@ int orc_num_threads(void) {
 #endif
 }
 
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 void orc_default_params(orc_params *p) {
   p->score_threshold = 0.6;       /* optimization.h:16 */
   p->minimum_visible_image = 3;   /* optimization.h:17 */

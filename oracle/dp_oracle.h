@@ -192,6 +192,8 @@ long long orc_expand_patches_fifo(orc_organizer *o, int cell_size, long long max
 long long orc_expand_patches(orc_organizer *o, int cell_size, int max_levels);
 
 int orc_num_threads(void);
+/* overrides OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1 to its workers) */
+void orc_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

@@ -362,5 +362,16 @@ def get_homography_mode() -> int:
     return lib().orc_get_homography_mode()
 
 
+def use_all_cores():
+    """Use every core this process may run on, whatever OMP_NUM_THREADS says (torchrun sets it
+    to 1 for its workers)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().orc_set_num_threads(C.c_int(n))
+    return num_threads()
+
+
 def num_threads():
     return lib().orc_num_threads()
