@@ -201,3 +201,100 @@ def test_filter_refine_fused_equals_two_calls(c1):
     assert np.array_equal(keep, k2) and np.array_equal(nvis, nv2) and np.array_equal(vis, vis2)
     assert np.array_equal(pos[m], p2) and np.array_equal(nrm[m], n2) and np.array_equal(evals[m], e2)
     assert np.array_equal(pos[~m], sd["pos"][~m]) and (evals[~m] == 0).all()
+
+
+@pytest.fixture(scope="module")
+def many_views(capi_mod, exact_orc):
+    """40 views: visible sets longer than one set-up round (16) and than one warp (32)."""
+    from densepoints_b200 import scenes
+    sc = scenes.make_plane_scene(seed=21, n_views=40, width=200, height=150, yaw_spread_deg=30.0)
+    seeds = scenes.make_seeds(sc, 400, seed=22, depth_noise=0.004, tilt_deg=6.0)
+    ctx = capi_mod.Context(0)
+    ctx.set_views(sc.P, sc.images)
+    V = exact_orc.Views(sc.P, sc.images)
+    nvis, vis, _, _ = exact_orc.visibility_batch(V, seeds["pos"], seeds["nrm"], seeds["ref"])
+    yield dict(sc=sc, seeds=seeds, ctx=ctx, V=V, nvis=nvis, vis=vis)
+    ctx.close()
+
+
+def test_many_views_multi_round(many_views, exact_orc):
+    d = many_views
+    sd = d["seeds"]
+    assert d["nvis"].max() > 32 and (d["nvis"] > 16).mean() > 0.5
+    g_nvis, g_vis, _, _ = d["ctx"].visibility(sd["pos"], sd["nrm"], sd["ref"])
+    assert np.array_equal(g_nvis, d["nvis"]) and np.array_equal(g_vis, d["vis"])
+    for s in (5, 7):
+        ncc, tex, valid = d["ctx"].score(sd["pos"], sd["nrm"], sd["ref"], d["nvis"], d["vis"], s,
+                                         want_tex=True)
+        o_ncc, o_tex, o_valid = exact_orc.score_batch(d["V"], sd["pos"], sd["nrm"], sd["ref"],
+                                                      d["nvis"], d["vis"], s, want_tex=True)
+        assert np.array_equal(valid, o_valid) and np.array_equal(tex, o_tex)
+        assert np.abs(ncc - o_ncc).max() < 1e-6
+        keep, nv, vi = d["ctx"].filter(sd["pos"], sd["nrm"], sd["ref"], d["nvis"], d["vis"], s)
+        o_keep, o_nv, o_vi = exact_orc.filter_batch(d["V"], sd["pos"], sd["nrm"], sd["ref"],
+                                                    d["nvis"], d["vis"], s, 0.6, 3)
+        assert np.array_equal(keep, o_keep) and np.array_equal(nv, o_nv) and np.array_equal(vi, o_vi)
+        assert (nv < d["nvis"]).any() and keep.any()
+    n = 80
+    pos, nrm, ev, xb = d["ctx"].refine(sd["pos"][:n], sd["nrm"][:n], sd["ref"][:n], d["nvis"][:n],
+                                       d["vis"][:n], 5)
+    o_pos, o_nrm, o_ev, o_xb = exact_orc.refine_batch(d["V"], sd["pos"][:n], sd["nrm"][:n],
+                                                      sd["ref"][:n], d["nvis"][:n], d["vis"][:n], 5)
+    assert np.array_equal(ev, o_ev) and np.array_equal(pos, o_pos) and np.array_equal(nrm, o_nrm)
+
+
+def test_large_roi_takes_the_unstaged_path(capi_mod, exact_orc):
+    """A view three times closer than the reference view: its ROI exceeds the shared-memory
+    tile (128 * passes pixels), so the texels are gathered straight from global memory."""
+    from densepoints_b200 import scenes
+    base = scenes.make_plane_scene(seed=31, n_views=3, width=640, height=480)
+    close = scenes.make_plane_scene(seed=32, n_views=1, width=640, height=480, distance=6.5,
+                                    f=640.0, extent=base.extent)
+    P = np.concatenate([base.P, close.P])
+    images = list(base.images) + list(close.images)
+    rng = np.random.default_rng(5)
+    n = 300
+    pos = np.stack([rng.uniform(-1.5, 1.5, n), rng.uniform(-1.0, 1.0, n),
+                    rng.uniform(-0.02, 0.02, n)], 1).astype(np.float32)
+    nrm = np.tile(np.array([0, 0, 1], np.float32), (n, 1))
+    ref = np.zeros(n, np.int32)
+    nvis = np.full(n, 3, np.int32)
+    vis = np.tile(np.array([1, 2, 3], np.int32), (n, 1))
+    ctx = capi_mod.Context(0)
+    ctx.set_views(P, images)
+    V = exact_orc.Views(P, images)
+    for s in (5, 7, 11):
+        ncc, tex, valid = ctx.score(pos, nrm, ref, nvis, vis, s, want_tex=True)
+        o_ncc, o_tex, o_valid = exact_orc.score_batch(V, pos, nrm, ref, nvis, vis, s, want_tex=True)
+        assert valid[:, 2].mean() > 0.5                     # the close view does see the patches
+        assert np.array_equal(valid, o_valid) and np.array_equal(tex, o_tex)
+        assert np.abs(ncc - o_ncc).max() < 1e-6
+    # the ROI in the close view really is larger than the tile for s = 5 (128 px) and 7 (256 px)
+    xa, ya, dx = exact_orc.axes_scale(V, 0, nrm[0].astype(np.float64), pos[0].astype(np.float64))
+    ok, H, roi = exact_orc.patch_homography(V, 3, 7, pos[0].astype(np.float64), 3 / dx * xa,
+                                            3 / dx * ya)
+    assert ok == 1 and roi[2] * roi[3] > 256
+    p2, n2, ev, _ = ctx.refine(pos[:60], nrm[:60], ref[:60], nvis[:60], vis[:60], 7)
+    o_p, o_n, o_ev, _ = exact_orc.refine_batch(V, pos[:60], nrm[:60], ref[:60], nvis[:60], vis[:60], 7)
+    assert np.array_equal(ev, o_ev) and np.array_equal(p2, o_p) and np.array_equal(n2, o_n)
+    ctx.close()
+
+
+def test_params_and_error_paths(capi_mod, c1):
+    ctx = c1["ctx"]
+    p = ctx.get_params()
+    assert p.minimum_visible_image == 2 and p.score_threshold == 0.6
+    bad = capi_mod.default_params(max_patches_per_cell=2)
+    with pytest.raises(capi_mod.DpError):
+        ctx.set_params(bad)                                  # only 1 patch per cell is supported
+    with pytest.raises(capi_mod.DpError):
+        capi_mod.Context(0, capi_mod.default_params(grid_scale=0))
+    fresh = capi_mod.Context(0)
+    with pytest.raises(capi_mod.DpError):                    # no views uploaded yet
+        fresh.score(c1["seeds"]["pos"][:1], c1["seeds"]["nrm"][:1], c1["seeds"]["ref"][:1],
+                    c1["nvis"][:1], c1["vis"][:1], 5)
+    with pytest.raises(capi_mod.DpError):                    # organizer used before reset
+        fresh.organizer_size() or fresh.expand(5, 1)
+    fresh.close()
+    # stricter thresholds change the filter exactly as the oracle's
+    assert ctx.launch_count() > 0
