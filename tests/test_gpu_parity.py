@@ -298,3 +298,45 @@ def test_params_and_error_paths(capi_mod, c1):
     fresh.close()
     # stricter thresholds change the filter exactly as the oracle's
     assert ctx.launch_count() > 0
+
+
+def test_dark_textures_with_inexact_fp32_centring(capi_mod, exact_orc):
+    """Dark images with bright speckles: g_max - mean exceeds what fp32 represents exactly, so
+    the reference's `Mat - scalar` on CV_32F (error_measurements.cpp:54) really rounds; the
+    element-wise fp32 emulation must still match the oracle (an integer-moment shortcut would
+    not)."""
+    from densepoints_b200 import scenes
+    sc = scenes.make_plane_scene(seed=1, n_views=3, width=640, height=480)
+    images = []
+    for im in sc.images:
+        d = (im // 7).astype(np.uint8)
+        d[::5, ::7] = 255
+        d[1::5, 3::7] = 200
+        images.append(d)
+    seeds = scenes.make_seeds(sc, 1200, seed=8)
+    ctx = capi_mod.Context(0, capi_mod.default_params(minimum_visible_image=2))
+    ctx.set_views(sc.P, images)
+    V = exact_orc.Views(sc.P, images)
+    nvis, vis, _, _ = exact_orc.visibility_batch(V, seeds["pos"], seeds["nrm"], seeds["ref"])
+    hit = 0
+    for s in (5, 7, 11):
+        ncc, tex, valid = ctx.score(seeds["pos"], seeds["nrm"], seeds["ref"], nvis, vis, s,
+                                    want_tex=True)
+        o_ncc, o_tex, o_valid = exact_orc.score_batch(V, seeds["pos"], seeds["nrm"], seeds["ref"],
+                                                      nvis, vis, s, want_tex=True)
+        assert np.array_equal(tex, o_tex) and np.array_equal(valid, o_valid)
+        assert np.abs(ncc - o_ncc).max() < 1e-6
+        # how many textures really need the element-wise path
+        t64 = tex.astype(np.int64)
+        gray = (3735 * t64[..., 0] + 19235 * t64[..., 1] + 9798 * t64[..., 2] + (1 << 14)) >> 15
+        mean = gray.reshape(gray.shape[0], gray.shape[1], -1).mean(-1).astype(np.float32)
+        gmax = gray.reshape(gray.shape[0], gray.shape[1], -1).max(-1)
+        p2 = 2.0 ** (np.floor(np.log2(np.maximum(mean, 1e-9))) + 1)
+        hit += int(((gmax >= mean + p2) & (valid == 1)).sum())
+    assert hit > 100
+    n = 300
+    p, nr, ev, _ = ctx.refine(seeds["pos"][:n], seeds["nrm"][:n], seeds["ref"][:n], nvis[:n], vis[:n], 5)
+    op, on, oev, _ = exact_orc.refine_batch(V, seeds["pos"][:n], seeds["nrm"][:n], seeds["ref"][:n],
+                                            nvis[:n], vis[:n], 5)
+    assert np.array_equal(ev, oev) and np.array_equal(p, op) and np.array_equal(nr, on)
+    ctx.close()
