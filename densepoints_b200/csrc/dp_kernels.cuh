@@ -244,80 +244,84 @@ __device__ __forceinline__ void dp_unparametrize(const double *__restrict__ C, c
   n[2] = xadd(xadd(xmul(xmul(ca, sb), n0[0]), xmul(-sa, n0[1])), xmul(xmul(ca, cb), n0[2]));
 }
 
-// Nelder-Mead state of one patch (cv::DownhillSolver, ndim = 3), kept "in the lanes":
-// every lane owns one slot = a 3-vector plus a scalar (8 registers), so the whole solver
-// state costs 8 registers per thread instead of ~60 for warp-uniform copies.  Slots are read
-// with shuffles (a few dozen per Nelder-Mead step, against thousands of instructions per
-// objective evaluation).
-struct DpSlots {
-  double x, y, z, v;
-  __device__ __forceinline__ void get3(int slot, double o[3]) const {
-    o[0] = __shfl_sync(DP_FULL, x, slot);
-    o[1] = __shfl_sync(DP_FULL, y, slot);
-    o[2] = __shfl_sync(DP_FULL, z, slot);
-  }
-  __device__ __forceinline__ double getv(int slot) const { return __shfl_sync(DP_FULL, v, slot); }
-  __device__ __forceinline__ void set3(int slot, int lane, const double o[3]) {
-    if (lane == slot) { x = o[0]; y = o[1]; z = o[2]; }
-  }
-  __device__ __forceinline__ void setv(int slot, int lane, double val) {
-    if (lane == slot) v = val;
-  }
+// Nelder-Mead state of one patch (cv::DownhillSolver, ndim = 3), one instance per warp in
+// shared memory.  All lanes of the warp run the solver redundantly on identical values; the
+// state is read with broadcast loads and written by lane 0 between two __syncwarp()s.  Compared
+// with warp-uniform registers (~60 of them) this keeps the refine kernel at the register count
+// of the scoring loop, and compared with shuffle-based "lane slots" it keeps the solver code
+// small: the kernel is instruction-cache sensitive (profiles/r01_summary.md).
+struct DpNelderMead {
+  double P[4][3];   // simplex vertices
+  double y[4];      // objective at the vertices
+  double cs[3];     // coord_sum
+  double pa[3];     // accepted reflection point
+  double pt[3];     // point being evaluated
+  double n0[3], p0[3], c3[3];  // patch normal / position at entry, reference camera centre
+  double y_alpha, y_lo, y_nhi, y_hi;
 };
-// slots 0..3: simplex vertices (v = objective there)
-#define SL_PA 4   // accepted reflection point, v = y_alpha
-#define SL_PT 5   // point being evaluated
-#define SL_CS 6   // coord_sum
-#define SL_YS 7   // x = y_lo, y = y_nhi, z = y_hi of the current iteration
-#define SL_N0 8   // patch normal at entry
-#define SL_P0 9   // patch position at entry
-#define SL_C 10   // camera centre of the reference view
 
-// coord_sum = sum of the vertices, accumulated in vertex order (updateCoordSum)
-__device__ __forceinline__ void dp_coord_sum(DpSlots &S, int lane) {
-  double t[3] = {0.0, 0.0, 0.0}, q[3];
-#pragma unroll
-  for (int v = 0; v < 4; ++v) {
-    S.get3(v, q);
-#pragma unroll
-    for (int j = 0; j < 3; ++j) t[j] = xadd(t[j], q[j]);
-  }
-  S.set3(SL_CS, lane, t);
+__device__ __forceinline__ void nm_store3(double *dst, const double v[3], int lane) {
+  __syncwarp();
+  if (lane == 0) { dst[0] = v[0]; dst[1] = v[1]; dst[2] = v[2]; }
+  __syncwarp();
 }
 
-// tryNewPoint / replacePoint: ptry = coord_sum * (1-a)/n - p_hi * ((1-a)/n - a)  -> SL_PT
-__device__ __forceinline__ void dp_try_point(DpSlots &S, int lane, int ihi, double alpha_) {
+// coord_sum = sum of the vertices, accumulated in vertex order (updateCoordSum)
+__device__ __forceinline__ void nm_coord_sum(DpNelderMead &S, int lane) {
+  double t[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+    t[j] = xadd(xadd(xadd(xadd(0.0, S.P[0][j]), S.P[1][j]), S.P[2][j]), S.P[3][j]);
+  nm_store3(S.cs, t, lane);
+}
+
+// tryNewPoint / replacePoint: ptry = coord_sum * (1-a)/n - p_hi * ((1-a)/n - a)  -> S.pt
+__device__ __forceinline__ void nm_try_point(DpNelderMead &S, int lane, int ihi, double alpha_) {
   const double al = (1.0 - alpha_) / 3.0;
   const double be = xsub(al, alpha_);
-  double cs[3], ph[3], pt[3];
-  S.get3(SL_CS, cs);
-  S.get3(ihi, ph);
+  double pt[3];
 #pragma unroll
-  for (int j = 0; j < 3; ++j) pt[j] = xsub(xmul(cs[j], al), xmul(ph[j], be));
-  S.set3(SL_PT, lane, pt);
+  for (int j = 0; j < 3; ++j) pt[j] = xsub(xmul(S.cs[j], al), xmul(S.P[ihi][j], be));
+  nm_store3(S.pt, pt, lane);
+}
+
+// replacePoint: vertex ihi <- q with objective yq, then updateCoordSum
+__device__ __forceinline__ void nm_replace(DpNelderMead &S, int lane, int ihi, const double q[3],
+                                           double yq) {
+  __syncwarp();
+  if (lane == 0) {
+    S.P[ihi][0] = q[0]; S.P[ihi][1] = q[1]; S.P[ihi][2] = q[2];
+    S.y[ihi] = yq;
+  }
+  __syncwarp();
+  nm_coord_sum(S, lane);
 }
 
 // vertex idx <- halfway to vertex ilo (the shrink step); also becomes the point to evaluate
-__device__ __forceinline__ void dp_shrink_vertex(DpSlots &S, int lane, int idx, int ilo) {
-  double pi[3], pl[3], pt[3];
-  S.get3(idx, pi);
-  S.get3(ilo, pl);
+__device__ __forceinline__ void nm_shrink_vertex(DpNelderMead &S, int lane, int idx, int ilo) {
+  double pt[3];
 #pragma unroll
-  for (int j = 0; j < 3; ++j) pt[j] = xmul(0.5, xadd(pi[j], pl[j]));
-  S.set3(idx, lane, pt);
-  S.set3(SL_PT, lane, pt);
+  for (int j = 0; j < 3; ++j) pt[j] = xmul(0.5, xadd(S.P[idx][j], S.P[ilo][j]));
+  __syncwarp();
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { S.P[idx][j] = pt[j]; S.pt[j] = pt[j]; }
+  }
+  __syncwarp();
 }
 
 template <int NPASS>
 __global__ void __launch_bounds__(DP_RWARPS * 32, dp_refine_min_ctas(NPASS)) dp_refine_kernel(DpRefineArgs a) {
   __shared__ uint32_t tiles[DP_RWARPS][DpTileCfg<NPASS>::kTilePx];
   __shared__ DpViewSetup recs[DP_RWARPS][DP_ROUND];
+  __shared__ DpNelderMead nm[DP_RWARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = a.p.s, npx = s * s;
   DpTexels<NPASS> tx;
   tx.init(s, lane);
   uint32_t *tile = tiles[warp];
-  enum { ST_INIT, ST_REFLECT, ST_EXPAND, ST_CONTRACT, ST_SHRINK };
+  DpNelderMead &S = nm[warp];
+  enum { ST_INIT, ST_REFLECT, ST_EXPAND, ST_CONTRACT, ST_SHRINK, ST_DONE };
   for (;;) {
     unsigned int iu = 0;
     if (lane == 0) iu = atomicAdd(a.work_counter, 1u);
@@ -332,35 +336,52 @@ __global__ void __launch_bounds__(DP_RWARPS * 32, dp_refine_min_ctas(NPASS)) dp_
     const int ref = a.p.ref[i];
     const bool ref_ok = ref >= 0 && ref < a.p.n_views;
     const int32_t *vis = a.p.vis + (size_t)i * a.p.vstride;
-    DpSlots S;
-    {
+    __syncwarp();
+    if (lane == 0) {
       // createInitialSimplex: v_i = x0 + step_{i-1}/2 e_{i-1}, then v_0 = x0 - step/2; x0 = 0
-      const double h0 = xmul(0.5, a.step[0]), h1 = xmul(0.5, a.step[1]), h2 = xmul(0.5, a.step[2]);
-      S.x = lane == 0 ? xsub(0.0, h0) : (lane == 1 ? xadd(0.0, h0) : 0.0);
-      S.y = lane == 0 ? xsub(0.0, h1) : (lane == 2 ? xadd(0.0, h1) : 0.0);
-      S.z = lane == 0 ? xsub(0.0, h2) : (lane == 3 ? xadd(0.0, h2) : 0.0);
-      S.v = 0.0;
-      if (lane == SL_PT) { S.x = xsub(0.0, h0); S.y = xsub(0.0, h1); S.z = xsub(0.0, h2); }
-      if (lane == SL_N0) { S.x = (double)a.p.nrm[3 * i]; S.y = (double)a.p.nrm[3 * i + 1]; S.z = (double)a.p.nrm[3 * i + 2]; }
-      if (lane == SL_P0) { S.x = (double)a.p.pos[3 * i]; S.y = (double)a.p.pos[3 * i + 1]; S.z = (double)a.p.pos[3 * i + 2]; }
-      if (lane == SL_C) {
-        const double *C = a.p.views[ref_ok ? ref : 0].center;
-        S.x = C[0]; S.y = C[1]; S.z = C[2];
+      const double *C = a.p.views[ref_ok ? ref : 0].center;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const double h = xmul(0.5, a.step[j]);
+        S.P[0][j] = xsub(0.0, h);
+        S.pt[j] = xsub(0.0, h);
+#pragma unroll
+        for (int v = 1; v < 4; ++v) S.P[v][j] = (v - 1 == j) ? xadd(0.0, h) : 0.0;
+        S.n0[j] = (double)a.p.nrm[3 * i + j];
+        S.p0[j] = (double)a.p.pos[3 * i + j];
+        S.c3[j] = C[j];
       }
     }
+    __syncwarp();
     int state = ST_INIT, idx = 0, fcount = 4;
     int ilo = 0, ihi = 0;
 #pragma unroll 1
     for (;;) {
+      // UnparametrizePatch at the point to evaluate (or, in ST_DONE, at the best vertex)
+      double n[3], p[3];
+      {
+        const double c3[3] = {S.c3[0], S.c3[1], S.c3[2]};
+        const double n0[3] = {S.n0[0], S.n0[1], S.n0[2]};
+        const double p0[3] = {S.p0[0], S.p0[1], S.p0[2]};
+        dp_unparametrize(c3, n0, p0, S.pt[0], S.pt[1], S.pt[2], n, p);
+      }
+      if (state == ST_DONE) {
+        // SetNormal / SetPosition store fp32 (patch.h:38-53)
+        if (lane < 3) {
+          const double nv_ = lane == 0 ? n[0] : (lane == 1 ? n[1] : n[2]);
+          const double pv_ = lane == 0 ? p[0] : (lane == 1 ? p[1] : p[2]);
+          if (ref_ok) {
+            a.p.nrm[3 * i + lane] = (float)nv_;
+            a.p.pos[3 * i + lane] = (float)pv_;
+          }
+          if (a.xbest) a.xbest[3 * i + lane] = S.pt[lane];
+        }
+        if (a.evals && lane == 0) a.evals[i] = fcount;
+        break;
+      }
       // ---- the single objective call site: PatchOptimizationOpenCVFunctor::calc ----------
       double fval = 2.0;  // scores.size() == 0 (optimization_opencv.cpp:30-32)
       if (nv >= 2 && ref_ok) {
-        double pt[3], n0[3], p0[3], c3[3], n[3], p[3];
-        S.get3(SL_PT, pt);
-        S.get3(SL_N0, n0);
-        S.get3(SL_P0, p0);
-        S.get3(SL_C, c3);
-        dp_unparametrize(c3, n0, p0, pt[0], pt[1], pt[2], n, p);
         double sum = 0.0;
         dp_eval_views<NPASS, false>(
             a.p.views, a.p.n_views, ref, vis, nv, s, npx, n, p, tx, tile, recs[warp], lane,
@@ -375,81 +396,73 @@ __global__ void __launch_bounds__(DP_RWARPS * 32, dp_refine_min_ctas(NPASS)) dp_
       // ---- consume it according to the Nelder-Mead state ---------------------------------
       bool decide = false;
       if (state == ST_INIT) {
-        S.setv(idx, lane, fval);
+        __syncwarp();
+        if (lane == 0) S.y[idx] = fval;
+        __syncwarp();
         if (++idx < 4) {
-          double q[3];
-          S.get3(idx, q);
-          S.set3(SL_PT, lane, q);
+          const double q[3] = {S.P[idx][0], S.P[idx][1], S.P[idx][2]};
+          nm_store3(S.pt, q, lane);
         } else {
-          dp_coord_sum(S, lane);
+          nm_coord_sum(S, lane);
           decide = true;
         }
       } else if (state == ST_REFLECT) {
-        const double y_lo = __shfl_sync(DP_FULL, S.x, SL_YS), y_nhi = __shfl_sync(DP_FULL, S.y, SL_YS);
-        double q[3];
-        S.get3(SL_PT, q);
-        S.set3(SL_PA, lane, q);
-        S.setv(SL_PA, lane, fval);  // y_alpha
+        const double q[3] = {S.pt[0], S.pt[1], S.pt[2]};
+        const double y_lo = S.y_lo, y_nhi = S.y_nhi;
+        __syncwarp();
+        if (lane == 0) {
+          S.pa[0] = q[0]; S.pa[1] = q[1]; S.pa[2] = q[2];
+          S.y_alpha = fval;
+        }
+        __syncwarp();
         if (fval < y_nhi) {
           if (fval < y_lo) {  // better than the best: try twice as far
             state = ST_EXPAND;
-            dp_try_point(S, lane, ihi, -2.0);
+            nm_try_point(S, lane, ihi, -2.0);
             ++fcount;
           } else {
-            S.set3(ihi, lane, q);  // replacePoint(alpha = -1)
-            S.setv(ihi, lane, fval);
-            dp_coord_sum(S, lane);
+            nm_replace(S, lane, ihi, q, fval);  // replacePoint(alpha = -1)
             decide = true;
           }
         } else {
           state = ST_CONTRACT;
-          dp_try_point(S, lane, ihi, 0.5);
+          nm_try_point(S, lane, ihi, 0.5);
           ++fcount;
         }
       } else if (state == ST_EXPAND) {
-        double y_alpha = S.getv(SL_PA);
-        double q[3];
-        if (fval < y_alpha) {
-          y_alpha = fval;
-          S.get3(SL_PT, q);
-        } else {
-          S.get3(SL_PA, q);
-        }
-        S.set3(ihi, lane, q);
-        S.setv(ihi, lane, y_alpha);
-        dp_coord_sum(S, lane);
+        const double y_alpha = S.y_alpha;
+        const bool better = fval < y_alpha;
+        const double q[3] = {better ? S.pt[0] : S.pa[0], better ? S.pt[1] : S.pa[1],
+                             better ? S.pt[2] : S.pa[2]};
+        nm_replace(S, lane, ihi, q, better ? fval : y_alpha);
         decide = true;
       } else if (state == ST_CONTRACT) {
-        const double y_hi = __shfl_sync(DP_FULL, S.z, SL_YS);
-        if (fval < y_hi) {
-          double q[3];
-          S.get3(SL_PT, q);
-          S.set3(ihi, lane, q);
-          S.setv(ihi, lane, fval);
-          dp_coord_sum(S, lane);
+        if (fval < S.y_hi) {
+          const double q[3] = {S.pt[0], S.pt[1], S.pt[2]};
+          nm_replace(S, lane, ihi, q, fval);
           decide = true;
         } else {  // shrink every vertex but the best halfway towards it
           state = ST_SHRINK;
           idx = (ilo == 0) ? 1 : 0;
-          dp_shrink_vertex(S, lane, idx, ilo);
+          nm_shrink_vertex(S, lane, idx, ilo);
         }
       } else {  // ST_SHRINK
-        S.setv(idx, lane, fval);
+        __syncwarp();
+        if (lane == 0) S.y[idx] = fval;
+        __syncwarp();
         ++idx;
         if (idx == ilo) ++idx;
         if (idx < 4) {
-          dp_shrink_vertex(S, lane, idx, ilo);
+          nm_shrink_vertex(S, lane, idx, ilo);
         } else {
           fcount += 3;
-          dp_coord_sum(S, lane);
+          nm_coord_sum(S, lane);
           decide = true;
         }
       }
       if (!decide) continue;
       // ---- find worst, next-to-worst and best vertices; stop test ------------------------
-      double yv[4];
-#pragma unroll
-      for (int v = 0; v < 4; ++v) yv[v] = S.getv(v);
+      const double yv[4] = {S.y[0], S.y[1], S.y[2], S.y[3]};
       int inhi;
       double ylo = yv[0], yhi, ynhi;
       ilo = 0;
@@ -468,45 +481,27 @@ __global__ void __launch_bounds__(DP_RWARPS * 32, dp_refine_min_ctas(NPASS)) dp_
           if (yv[v] == ylo && v != ihi && v != inhi) ilo = v;
       }
       const double error = fabs(xsub(yhi, ylo));
-      // range = max over coordinates of (max - min) over the 4 vertices = lanes 0..3 (the
-      // xor-1/2 butterflies stay inside that group; other groups compute garbage, unused)
-      double range;
-      {
-        double mnx = S.x, mxx = S.x, mny = S.y, mxy = S.y, mnz = S.z, mxz = S.z;
+      double range = 0.0;
 #pragma unroll
-        for (int o = 1; o <= 2; o <<= 1) {
-          mnx = fmin(mnx, __shfl_xor_sync(DP_FULL, mnx, o));
-          mxx = fmax(mxx, __shfl_xor_sync(DP_FULL, mxx, o));
-          mny = fmin(mny, __shfl_xor_sync(DP_FULL, mny, o));
-          mxy = fmax(mxy, __shfl_xor_sync(DP_FULL, mxy, o));
-          mnz = fmin(mnz, __shfl_xor_sync(DP_FULL, mnz, o));
-          mxz = fmax(mxz, __shfl_xor_sync(DP_FULL, mxz, o));
-        }
-        range = fmax(fabs(xsub(mxx, mnx)), fmax(fabs(xsub(mxy, mny)), fabs(xsub(mxz, mnz))));
-        range = __shfl_sync(DP_FULL, range, 0);
+      for (int j = 0; j < 3; ++j) {
+        double mn = S.P[0][j], mx = S.P[0][j];
+#pragma unroll
+        for (int v = 1; v < 4; ++v) { mn = fmin(mn, S.P[v][j]); mx = fmax(mx, S.P[v][j]); }
+        range = fmax(range, fabs(xsub(mx, mn)));
       }
-      if (range <= a.eps || error <= a.eps || fcount >= a.max_evals) break;
-      if (lane == SL_YS) { S.x = ylo; S.y = ynhi; S.z = yhi; }
+      if (range <= a.eps || error <= a.eps || fcount >= a.max_evals) {
+        // best vertex -> x: one more trip through UnparametrizePatch, then write back
+        const double q[3] = {S.P[ilo][0], S.P[ilo][1], S.P[ilo][2]};
+        nm_store3(S.pt, q, lane);
+        state = ST_DONE;
+        continue;
+      }
+      __syncwarp();
+      if (lane == 0) { S.y_lo = ylo; S.y_nhi = ynhi; S.y_hi = yhi; }
+      __syncwarp();
       state = ST_REFLECT;  // reflect the worst point about the centroid of the others
-      dp_try_point(S, lane, ihi, -1.0);
+      nm_try_point(S, lane, ihi, -1.0);
       ++fcount;
     }
-    // best vertex -> x; UnparametrizePatch; SetNormal / SetPosition store fp32
-    double xb[3], n0[3], p0[3], c3[3], n[3], p[3];
-    S.get3(ilo, xb);
-    S.get3(SL_N0, n0);
-    S.get3(SL_P0, p0);
-    S.get3(SL_C, c3);
-    dp_unparametrize(c3, n0, p0, xb[0], xb[1], xb[2], n, p);
-    if (lane < 3) {
-      const double nv_ = lane == 0 ? n[0] : (lane == 1 ? n[1] : n[2]);
-      const double pv_ = lane == 0 ? p[0] : (lane == 1 ? p[1] : p[2]);
-      if (ref_ok) {
-        a.p.nrm[3 * i + lane] = (float)nv_;
-        a.p.pos[3 * i + lane] = (float)pv_;
-      }
-      if (a.xbest) a.xbest[3 * i + lane] = lane == 0 ? xb[0] : (lane == 1 ? xb[1] : xb[2]);
-    }
-    if (a.evals && lane == 0) a.evals[i] = fcount;
   }
 }
