@@ -4,6 +4,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <cuda.h>  // CUtensorMap types only; the encoder is fetched through the runtime
+
 #include <algorithm>
 
 #include "dp_aux_kernels.cuh"
@@ -22,6 +24,38 @@ int dp_fail(dp_context *ctx, int code, const char *what, cudaError_t e) {
     }
   }
   return code;
+}
+
+// A 2-D tensor map over one packed-BGRx image level: u32 elements, DP_TMA_BOX^2 box, no
+// swizzle, zero fill outside the image.  The driver entry point is resolved through the CUDA
+// runtime so the library does not link libcuda.
+typedef CUresult (*dp_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                       const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                       const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+bool dp_encode_tmap(DpLevel &l) {
+  static dp_encode_tiled_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (dp_encode_tiled_fn)p;
+  }
+  l.has_tmap = false;
+  if (!fn) return false;
+  static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+  const cuuint64_t dims[2] = {(cuuint64_t)l.pitch_px, (cuuint64_t)l.height};
+  const cuuint64_t strides[1] = {(cuuint64_t)l.pitch_px * 4};
+  const cuuint32_t box[2] = {DP_TMA_BOX, DP_TMA_BOX};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(reinterpret_cast<CUtensorMap *>(l.tmap), CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, l.img, dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  l.has_tmap = (r == CUDA_SUCCESS);
+  return l.has_tmap;
 }
 
 static int npass_for(int s) {
@@ -101,7 +135,7 @@ extern "C" void dp_destroy(dp_context *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   free_views(ctx);
-  DpDevBuf *bufs[] = {&ctx->d_views, &ctx->s_pos, &ctx->s_nrm, &ctx->s_ref, &ctx->s_nvis,
+  DpDevBuf *bufs[] = {&ctx->d_views, &ctx->d_tmaps, &ctx->s_pos, &ctx->s_nrm, &ctx->s_ref, &ctx->s_nvis,
                       &ctx->s_vis, &ctx->s_rgb, &ctx->s_ncc, &ctx->s_tex, &ctx->s_valid,
                       &ctx->s_keep, &ctx->s_evals, &ctx->s_xbest, &ctx->s_cand, &ctx->s_ncand,
                       &ctx->s_img, &ctx->s_misc, &ctx->work_counter, &ctx->s_order, &ctx->e_pos, &ctx->e_nrm,
@@ -219,6 +253,7 @@ extern "C" int dp_upload_view(dp_context *ctx, int view_id, const double P[12], 
   l.height = height;
   l.pitch_px = (width + 31) & ~31;  // 128-byte aligned rows
   DP_CUDA(ctx, cudaMalloc(&l.img, (size_t)l.pitch_px * height * sizeof(uint32_t)));
+  dp_encode_tmap(l);
   v.levels.push_back(l);
   const size_t bytes = stride * (size_t)height;
   DP_CUDA(ctx, ctx->s_img.ensure(bytes));
@@ -257,6 +292,8 @@ int dp_sync_views(dp_context *ctx) {
   const int nv = (int)ctx->views.size();
   if (nv == 0) return dp_fail(ctx, DP_ERR_STATE, "no views uploaded");
   std::vector<DpViewDev> h(nv);
+  std::vector<unsigned char> tm((size_t)nv * 128);
+  DP_CUDA(ctx, ctx->d_tmaps.ensure((size_t)nv * 128));
   long long off = 0;
   for (int i = 0; i < nv; ++i) {
     const DpViewHost &v = ctx->views[i];
@@ -272,6 +309,8 @@ int dp_sync_views(dp_context *ctx) {
       h[i].center[j] = v.center[j];
     }
     h[i].img = l.img;
+    memcpy(tm.data() + (size_t)i * 128, l.tmap, 128);
+    h[i].tmap = l.has_tmap ? (const void *)(ctx->d_tmaps.as<unsigned char>() + (size_t)i * 128) : nullptr;
     h[i].width = l.width;
     h[i].height = l.height;
     h[i].pitch_px = l.pitch_px;
@@ -283,6 +322,8 @@ int dp_sync_views(dp_context *ctx) {
   DP_CUDA(ctx, ctx->d_views.ensure(sizeof(DpViewDev) * nv));
   DP_CUDA(ctx, cudaMemcpyAsync(ctx->d_views.ptr, h.data(), sizeof(DpViewDev) * nv,
                                cudaMemcpyHostToDevice, ctx->stream));
+  DP_CUDA(ctx, cudaMemcpyAsync(ctx->d_tmaps.ptr, tm.data(), tm.size(), cudaMemcpyHostToDevice,
+                               ctx->stream));
   DP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->org.n_cells = off;
   ctx->views_dirty = false;

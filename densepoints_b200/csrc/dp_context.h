@@ -34,6 +34,8 @@ struct DpDevBuf {  // grow-only device scratch
 struct DpLevel {  // one pyramid level of one view
   uint32_t *img = nullptr;
   int width = 0, height = 0, pitch_px = 0;
+  alignas(64) unsigned char tmap[128];  // CUtensorMap: u32 [height][pitch_px], 16x16 box
+  bool has_tmap = false;
 };
 
 struct DpViewHost {
@@ -65,6 +67,7 @@ struct dp_context {
   dp_params prm;
   std::vector<DpViewHost> views;
   DpDevBuf d_views;      // DpViewDev[n_views] of the active level
+  DpDevBuf d_tmaps;      // CUtensorMap[n_views] of the active level (128 B each)
   bool views_dirty = true;
   int level = 0;
   int n_levels = 1;
@@ -83,7 +86,8 @@ struct dp_context {
 
 // internal helpers shared by the translation units
 int dp_fail(dp_context *ctx, int code, const char *what, cudaError_t e = cudaSuccess);
-int dp_sync_views(dp_context *ctx);  // (re)builds the DpViewDev table for the active level
+int dp_sync_views(dp_context *ctx);
+bool dp_encode_tmap(DpLevel &l);  // fills l.tmap (cuTensorMapEncodeTiled via the runtime)  // (re)builds the DpViewDev table for the active level
 #define DP_CUDA(ctx, call)                                             \
   do {                                                                 \
     cudaError_t e__ = (call);                                          \

@@ -25,6 +25,7 @@ struct DpViewDev {
   double xa[3];      // View::GetXAxis().normalized()
   double center[3];  // View::GetCameraCenter()
   const uint32_t *img;  // packed BGRx, pitch_px pixels per row
+  const void *tmap;     // CUtensorMap (global memory): 2-D u32 tensor, DP_TMA_BOX^2 box; or null
   int width, height, pitch_px;
   int gw, gh;              // PatchGrid dims: width / grid_scale, height / grid_scale
   long long grid_off;      // offset of this view's grid in the occupancy array
@@ -142,18 +143,72 @@ struct __align__(16) DpViewSetup {
   double M[8];          // source = (M0 x + M1 y + M2, M3 x + M4 y + M5) / (M6 x + M7 y + 1),
                         // in 1/32-px units (pre-scaled by INTER_TAB_SIZE), relative to the ROI
   const uint32_t *src;  // first pixel of the ROI (packed BGRx)
+  const void *tmap;     // tensor map of the view when the ROI fits one TMA box, else null
   int pitch, rw, rh;    // image pitch (pixels), ROI width / height
   int ok;               // 0 where the reference pushes an empty cv::Mat
   int lgp;              // log2 of the staged tile's row pitch (next power of two >= rw)
-  int pad;
+  int tlx, tly;         // TMA tile coordinates: tlx is the ROI origin rounded down to 4 px
+  int xoff;             // ROI origin - tlx (0..3): column of the ROI inside the staged tile
 };
-static_assert(sizeof(DpViewSetup) == 96, "DpViewSetup layout");
+static_assert(sizeof(DpViewSetup) == 112, "DpViewSetup layout");
+
+// ---- TMA (cp.async.bulk.tensor) staging of a patch footprint -----------------------------
+// A footprint of up to DP_TMA_BOX x DP_TMA_BOX pixels is tile-local: one elected lane issues
+// a single 2-D tensor copy of a fixed box anchored at the ROI origin (out-of-image elements
+// are zero-filled and never read) and the warp waits on an mbarrier; the copy of the next
+// view is issued before the current view is computed, so its latency is hidden.
+// Measured on B200 (tools/probe/tma_probe2.cu): the innermost tile coordinate times the
+// element size must be a multiple of 16 bytes, otherwise the copy raises "illegal
+// instruction" -- so the box starts at the ROI origin rounded down to 4 pixels.
+#define DP_TMA_BOX 16
+#define DP_TMA_LGP 4
+#define DP_TMA_BYTES (DP_TMA_BOX * DP_TMA_BOX * 4)
+
+__device__ __forceinline__ uint32_t dp_smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void dp_mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dp_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void dp_mbar_init_fence() {
+  // make the initialised barrier visible to the async (TMA) proxy; CTA scope is enough (a
+  // cluster-scope fence would also invalidate L1 at every CTA start)
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void dp_tma_load_tile(uint32_t *dst, const void *tmap, int x, int y,
+                                                 uint64_t *bar) {
+  const uint32_t b = dp_smem_u32(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b),
+               "r"((unsigned)DP_TMA_BYTES)
+               : "memory");
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3}], [%4];" ::"r"(dp_smem_u32(dst)),
+      "l"(tmap), "r"(x), "r"(y), "r"(b)
+      : "memory");
+}
+__device__ __forceinline__ void dp_mbar_wait(uint64_t *bar, unsigned parity) {
+  const uint32_t b = dp_smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(b), "r"(parity)
+        : "memory");
+  } while (!done);
+}
 
 #define DP_ROUND 16  // views whose set-up records are resident at once (per warp)
 
 __device__ __forceinline__ void dp_setup_views(const DpViewDev *__restrict__ views, int n_views,
                                                const int32_t *vis, int kcount, int s,
-                                               const DpFrame &f, DpViewSetup *recs, int lane) {
+                                               const DpFrame &f, DpViewSetup *recs, int lane,
+                                               bool use_tma) {
   const int c = lane & 3, slot = lane >> 2;
   const double sgx = (c == 1 || c == 2) ? 1.0 : -1.0;  // corners (-,-) (+,-) (+,+) (-,+),
   const double sgy = (c >= 2) ? 1.0 : -1.0;            // patch.cpp:119-123
@@ -220,7 +275,14 @@ __device__ __forceinline__ void dp_setup_views(const DpViewDev *__restrict__ vie
       R.rw = rw;
       R.rh = rh;
       R.ok = ok ? 1 : 0;
-      R.lgp = 32 - __clz(max(rw, 1) - 1);  // ceil(log2(rw))
+      const int xoff = tlx & 3;
+      const bool fits = ok && use_tma && V->tmap != nullptr && rw + xoff <= DP_TMA_BOX &&
+                        rh <= DP_TMA_BOX;
+      R.tmap = fits ? V->tmap : nullptr;
+      R.lgp = fits ? DP_TMA_LGP : 32 - __clz(max(rw, 1) - 1);  // ceil(log2(rw))
+      R.tlx = tlx - xoff;
+      R.tly = tly;
+      R.xoff = fits ? xoff : 0;
     }
   }
 }
@@ -228,30 +290,36 @@ __device__ __forceinline__ void dp_setup_views(const DpViewDev *__restrict__ vie
 // ---------------------------------------------------------------------------------------
 // Phase B: the texture of one view from its set-up record: gray value of every texel owned
 // by this lane (g[j], 0..255), optionally the BGR texels themselves.  `tile` is this warp's
-// shared-memory staging buffer of tile_cap pixels.
+// shared-memory staging buffer of tile_cap pixels; with pre_staged the ROI is already there
+// (TMA, row pitch 2^R.lgp).
+
+// Generic staging: tile rows padded to a power-of-two pitch so the flat index splits with a
+// shift and a mask; each 32-lane step loads 32/pitch whole rows with 32-bit loads.
+__device__ __forceinline__ bool dp_stage_roi(const DpViewSetup &R, uint32_t *tile, int tile_cap,
+                                             int lane) {
+  const int lgp = R.lgp, rw = R.rw, pitch = R.pitch;
+  const int area = R.rh << lgp;
+  if (area > tile_cap) return false;
+  const uint32_t *__restrict__ src = R.src;
+  const int cmask = (1 << lgp) - 1;
+  for (int t = lane; t < area; t += 32) {
+    const int r = t >> lgp, c = t & cmask;
+    if (c < rw) tile[t] = __ldg(src + (unsigned)(r * pitch + c));
+  }
+  __syncwarp();
+  return true;
+}
+
 template <int NPASS, bool WRITE_TEX>
 __device__ __forceinline__ void dp_view_texture(const DpViewSetup &R, int npx,
-                                                const DpTexels<NPASS> &tx, uint32_t *tile,
-                                                int tile_cap, int lane, int (&g)[NPASS],
+                                                const DpTexels<NPASS> &tx, const uint32_t *tile0,
+                                                bool staged, int lane, int (&g)[NPASS],
                                                 uint8_t *__restrict__ tex_out) {
+  const uint32_t *tile = tile0 + R.xoff;
   const double M0 = R.M[0], M1 = R.M[1], M2 = R.M[2], M3 = R.M[3], M4 = R.M[4], M5 = R.M[5],
                M6 = R.M[6], M7 = R.M[7];
   const uint32_t *__restrict__ src = R.src;
-  const int pitch = R.pitch, rw = R.rw, rh = R.rh;
-  // ---- stage the ROI into shared memory: tile rows padded to a power-of-two pitch so the
-  // flat index splits with a shift and a mask; each 32-lane step loads 32/pitch whole rows
-  // with 32-bit loads (one 128-B line per row for ROIs up to 32 px wide).
-  const int lgp = R.lgp;
-  const int area = rh << lgp;
-  const bool staged = area <= tile_cap;
-  if (staged) {
-    const int cmask = (1 << lgp) - 1;
-    for (int t = lane; t < area; t += 32) {
-      const int r = t >> lgp, c = t & cmask;
-      if (c < rw) tile[t] = __ldg(src + (unsigned)(r * pitch + c));
-    }
-    __syncwarp();
-  }
+  const int pitch = R.pitch, rw = R.rw, rh = R.rh, lgp = R.lgp;
   // ---- warp the texel grid ------------------------------------------------------------------
   // Branch-free: lanes past the last texel compute on a clamped (harmless) coordinate and are
   // masked at the end, so the NPASS independent passes can be interleaved by the scheduler.

@@ -45,11 +45,37 @@ struct DpScoreArgs {
   uint8_t *keep;
 };
 
-template <int NPASS>
+// TMA staging is a per-kernel choice (measured on B200, profiles/r01_summary.md): it pays in
+// the scoring / filter kernel (+2 %), not in the refine kernel (-3 %), whose warps are already
+// bound by fixed-latency dependencies rather than by the staging loop.
+template <int NPASS, bool TMA>
 struct DpTileCfg {
-  // 4x the texel count covers oblique / zoomed ROIs; capped at 4 KB per warp.  A larger
-  // ROI is gathered straight from global memory instead.
-  static constexpr int kTilePx = (128 * NPASS < 1024) ? 128 * NPASS : 1024;
+  // TMA: up to 4 texel passes (s <= 11) the footprint normally fits one 16x16 box: two 1 KB
+  // buffers per warp, the next view's box in flight while the current one is computed.
+  // Otherwise (and for ROIs that do not fit the box) the warp stages the ROI itself into one
+  // buffer of kTilePx pixels (~4x the texel count, for oblique / zoomed views) or, beyond
+  // that, gathers straight from global memory.
+  static constexpr bool kTma = TMA && NPASS <= 4;
+  static constexpr int kTilePx = kTma ? DP_TMA_BOX * DP_TMA_BOX : (128 * NPASS < 768 ? 128 * NPASS : 768);
+  static constexpr int kBufs = kTma ? 2 : 1;
+};
+
+// Per-warp shared memory of the score / refine kernels.
+template <int NPASS, bool TMA>
+struct __align__(128) DpWarpShared {
+  uint32_t tile[DpTileCfg<NPASS, TMA>::kBufs][DpTileCfg<NPASS, TMA>::kTilePx];
+  DpViewSetup recs[DP_ROUND];
+  uint64_t bar[2];
+  __device__ __forceinline__ void init(int lane) {
+    if (DpTileCfg<NPASS, TMA>::kTma) {
+      if (lane == 0) {
+        dp_mbar_init(&bar[0], 1);
+        dp_mbar_init(&bar[1], 1);
+        dp_mbar_init_fence();
+      }
+      __syncwarp();
+    }
+  }
 };
 
 // Evaluate all visible views of one patch at (n, p), DP_ROUND views per round:
@@ -59,13 +85,15 @@ struct DpTileCfg {
 // After each round sink(k0, kc, score) is called with lane l holding the score of view
 // k0 + l (l < kc; -1 when either texture is empty, error_measurements.cpp:38-40; the entry
 // of view 0 is meaningless).
-template <int NPASS, bool WRITE_TEX, typename Sink>
+template <int NPASS, bool WRITE_TEX, bool TMA, typename Sink>
 __device__ __forceinline__ void dp_eval_views(const DpViewDev *__restrict__ views, int n_views,
                                               int ref, const int32_t *vis, int nv, int s, int npx,
                                               const double n[3], const double p[3],
-                                              const DpTexels<NPASS> &tx, uint32_t *tile,
-                                              DpViewSetup *recs, int lane, uint8_t *tex_base,
+                                              const DpTexels<NPASS> &tx, DpWarpShared<NPASS, TMA> &ws,
+                                              unsigned &phase, int lane, uint8_t *tex_base,
                                               uint8_t *valid_base, Sink sink) {
+  constexpr bool kTma = DpTileCfg<NPASS, TMA>::kTma;
+  DpViewSetup *recs = ws.recs;
   DpFrame f;
   if (ref >= 0 && ref < n_views)
     dp_make_frame(views + ref, s, n, p, f);
@@ -79,8 +107,10 @@ __device__ __forceinline__ void dp_eval_views(const DpViewDev *__restrict__ view
   for (int k0 = 0; k0 < nv; k0 += DP_ROUND) {
     const int kc = min(DP_ROUND, nv - k0);
     __syncwarp();
-    dp_setup_views(views, n_views, vis + k0, kc, s, f, recs, lane);
+    dp_setup_views(views, n_views, vis + k0, kc, s, f, recs, lane, kTma);
     __syncwarp();
+    if (kTma && lane == 0 && recs[0].ok && recs[0].tmap != nullptr)  // first box of the round
+      dp_tma_load_tile(ws.tile[0], recs[0].tmap, recs[0].tlx, recs[0].tly, &ws.bar[0]);
     unsigned my1 = 0, my2 = 0;
     double mynum = 0.0;
     int myok = 0;
@@ -88,11 +118,25 @@ __device__ __forceinline__ void dp_eval_views(const DpViewDev *__restrict__ view
     for (int l = 0; l < kc; ++l) {
       const DpViewSetup &R = recs[l];
       const bool ok = R.ok != 0;  // warp-uniform
+      const int b = kTma ? (l & 1) : 0;
+      if (kTma && lane == 0 && l + 1 < kc) {  // next view's box goes into the other buffer
+        const DpViewSetup &Rn = recs[l + 1];
+        if (Rn.ok && Rn.tmap != nullptr)
+          dp_tma_load_tile(ws.tile[b ^ 1], Rn.tmap, Rn.tlx, Rn.tly, &ws.bar[b ^ 1]);
+      }
       unsigned s1 = 0, s2 = 0;
       double num = 0.0;
       if (ok) {
+        bool staged;
+        if (kTma && R.tmap != nullptr) {
+          dp_mbar_wait(&ws.bar[b], (phase >> b) & 1u);
+          phase ^= 1u << b;
+          staged = true;
+        } else {
+          staged = dp_stage_roi(R, ws.tile[b], DpTileCfg<NPASS, TMA>::kTilePx, lane);
+        }
         int g[NPASS];
-        dp_view_texture<NPASS, WRITE_TEX>(R, npx, tx, tile, DpTileCfg<NPASS>::kTilePx, lane, g,
+        dp_view_texture<NPASS, WRITE_TEX>(R, npx, tx, ws.tile[b], staged, lane, g,
                                           WRITE_TEX ? tex_base + (size_t)(k0 + l) * npx * 3
                                                     : nullptr);
         dp_moments<NPASS>(g, s1, s2);
@@ -126,11 +170,13 @@ __device__ __forceinline__ void dp_eval_views(const DpViewDev *__restrict__ view
 
 template <int NPASS, bool WRITE_TEX, bool FILTER>
 __global__ void __launch_bounds__(DP_WARPS * 32, dp_score_min_ctas(NPASS)) dp_score_kernel(DpScoreArgs a) {
-  __shared__ uint32_t tiles[DP_WARPS][DpTileCfg<NPASS>::kTilePx];
-  __shared__ DpViewSetup recs[DP_WARPS][DP_ROUND];
+  __shared__ DpWarpShared<NPASS, true> wsh[DP_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long i = (long long)blockIdx.x * DP_WARPS + warp;
   if (i >= a.p.n) return;
+  DpWarpShared<NPASS, true> &ws = wsh[warp];
+  ws.init(lane);
+  unsigned phase = 0;
   const int s = a.p.s, npx = s * s;
   DpTexels<NPASS> tx;
   tx.init(s, lane);
@@ -151,9 +197,9 @@ __global__ void __launch_bounds__(DP_WARPS * 32, dp_score_min_ctas(NPASS)) dp_sc
   int wcur = 0;
   const double thr = a.thr;
   const unsigned lt = (1u << lane) - 1u;
-  dp_eval_views<NPASS, WRITE_TEX>(
-      a.p.views, a.p.n_views, ref, vis, nv, s, npx, n, p, tx, tiles[warp], recs[warp], lane, tex,
-      valid, [&](int k0, int kc, double score) {
+  dp_eval_views<NPASS, WRITE_TEX, true>(
+      a.p.views, a.p.n_views, ref, vis, nv, s, npx, n, p, tx, ws, phase, lane, tex, valid,
+      [&](int k0, int kc, double score) {
         const int k = k0 + lane;
         const bool mine = lane < kc && k >= 1;
         if (ncc != nullptr && mine) ncc[k] = (float)score;
@@ -312,14 +358,15 @@ __device__ __forceinline__ void nm_shrink_vertex(DpNelderMead &S, int lane, int 
 
 template <int NPASS>
 __global__ void __launch_bounds__(DP_RWARPS * 32, dp_refine_min_ctas(NPASS)) dp_refine_kernel(DpRefineArgs a) {
-  __shared__ uint32_t tiles[DP_RWARPS][DpTileCfg<NPASS>::kTilePx];
-  __shared__ DpViewSetup recs[DP_RWARPS][DP_ROUND];
+  __shared__ DpWarpShared<NPASS, false> wsh[DP_RWARPS];
   __shared__ DpNelderMead nm[DP_RWARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = a.p.s, npx = s * s;
   DpTexels<NPASS> tx;
   tx.init(s, lane);
-  uint32_t *tile = tiles[warp];
+  DpWarpShared<NPASS, false> &ws = wsh[warp];
+  ws.init(lane);
+  unsigned phase = 0;
   DpNelderMead &S = nm[warp];
   enum { ST_INIT, ST_REFLECT, ST_EXPAND, ST_CONTRACT, ST_SHRINK, ST_DONE };
   for (;;) {
@@ -383,9 +430,9 @@ __global__ void __launch_bounds__(DP_RWARPS * 32, dp_refine_min_ctas(NPASS)) dp_
       double fval = 2.0;  // scores.size() == 0 (optimization_opencv.cpp:30-32)
       if (nv >= 2 && ref_ok) {
         double sum = 0.0;
-        dp_eval_views<NPASS, false>(
-            a.p.views, a.p.n_views, ref, vis, nv, s, npx, n, p, tx, tile, recs[warp], lane,
-            nullptr, nullptr, [&](int k0, int kc, double score) {
+        dp_eval_views<NPASS, false, false>(
+            a.p.views, a.p.n_views, ref, vis, nv, s, npx, n, p, tx, ws, phase, lane, nullptr,
+            nullptr, [&](int k0, int kc, double score) {
               // std::accumulate of (1 - NCC) in view order (optimization_opencv.cpp:24, 34)
               const double term = xsub(1.0, score);
               for (int l = (k0 == 0 ? 1 : 0); l < kc; ++l)

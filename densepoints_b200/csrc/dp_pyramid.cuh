@@ -65,6 +65,7 @@ extern "C" int dp_build_pyramid(dp_context *ctx, int n_levels) {
       dp_pyrdown_kernel<<<grid, 256, 0, st>>>(s.img, s.width, s.height, s.pitch_px, d.img, d.width,
                                               d.height, d.pitch_px);
       ++ctx->launches;
+      dp_encode_tmap(d);
       v.levels.push_back(d);
     }
   }
