@@ -4,6 +4,7 @@
 #ifndef DENSEPOINTS_B200_PMVS_EXPAND
 #define DENSEPOINTS_B200_PMVS_EXPAND
 
+#include <string>
 #include <vector>
 
 #include "densepoints/pmvs/optimization.h"
@@ -59,6 +60,11 @@ class Expand {
       out[i].SetTrullyVisibleImages(v);
     }
     return out;
+  }
+  // the point cloud as an ASCII PLY in the layout of PMVS::PrintCloud (utils.cpp:9-50); stands
+  // in for the declared-but-undefined PMVS::GetPointCloud (pmvs.h:21)
+  void WritePly(const std::string &path) {
+    session_->Check(dp_export_ply(session_->ctx(), path.c_str()), "dp_export_ply");
   }
   const int64_t *Stats() const { return stats_; }  // pops, candidates, passed, inserted
 

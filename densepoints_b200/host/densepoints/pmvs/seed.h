@@ -22,6 +22,38 @@ class SeedCUDA {
   void GetPatches(Patches &p) const { p = patches_; }
   Patches &patches() { return patches_; }
 
+  // Seed::CreatePatchesFromPoints (seed.cpp:26-54) for triangulated points: reference image =
+  // nearest camera centre, normal = unit viewing ray, InitRelatedImages; patch order = point
+  // order (the reference's omp-critical push_back order is racy).
+  void CreatePatchesFromPoints(const std::vector<Vector3> &points) {
+    const size_t n = points.size();
+    const int vs = (int)session_->views()->size();
+    std::vector<double> xyz(n * 3);
+    for (size_t i = 0; i < n; ++i)
+      for (int j = 0; j < 3; ++j) xyz[3 * i + j] = points[i][j];
+    std::vector<float> pos(n * 3), nrm(n * 3);
+    std::vector<int32_t> ref(n), nvis(n), vis(n * (size_t)vs, -1), ncand(n), cand(n * (size_t)vs, -1);
+    dp_patch_soa s;
+    s.n = (int32_t)n; s.vstride = vs;
+    s.pos = pos.data(); s.nrm = nrm.data(); s.ref = ref.data(); s.nvis = nvis.data();
+    s.vis = vis.data(); s.rgb = nullptr;
+    session_->Check(dp_create_patches(session_->ctx(), xyz.data(), (int)n, &s, ncand.data(), cand.data()),
+                    "dp_create_patches");
+    patches_.assign(n, Patch());
+    for (size_t i = 0; i < n; ++i) {
+      Patch &p = patches_[i];
+      p.SetReferenceImage((size_t)ref[i]);
+      PointXYZRGBNormal &q = p.Point();
+      q.x = pos[3 * i]; q.y = pos[3 * i + 1]; q.z = pos[3 * i + 2];
+      q.normal_x = nrm[3 * i]; q.normal_y = nrm[3 * i + 1]; q.normal_z = nrm[3 * i + 2];
+      ImagesIndices v, c;
+      for (int k = 0; k < nvis[i]; ++k) v.push_back((size_t)vis[i * vs + k]);
+      for (int k = 0; k < ncand[i] && k < vs; ++k) c.push_back((size_t)cand[i * vs + k]);
+      p.SetTrullyVisibleImages(v);
+      p.SetPotentiallyVisibleImages(c);
+    }
+  }
+
   // Patch::InitRelatedImages for every patch (seed.cpp:47)
   void InitRelatedImages() {
     if (patches_.empty()) return;

@@ -113,7 +113,16 @@ int main(int argc, char **argv) {
     expand.SetSeeds(refined, cfg[3]);
     dump(fo, expand.GetPatches(), n_views);
     wr(fo, expand.Stats(), 4);
+    // Seed::CreatePatchesFromPoints on the raw seed positions
+    {
+      std::vector<Vector3> pts;
+      for (int i = 0; i < n; ++i) pts.push_back(Vector3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]));
+      SeedCUDA created(session, cfg[0], 0.6, cfg[2]);
+      created.CreatePatchesFromPoints(pts);
+      dump(fo, created.patches(), n_views);
+    }
     fclose(fo);
+    if (argc > 3) expand.WritePly(argv[3]);
     std::printf("host mirror ok: %d seeds -> %zu refined -> %zu patches after expansion\n", n,
                 refined.size(), expand.GetPatches().size());
   } catch (const std::exception &e) {

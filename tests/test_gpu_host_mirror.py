@@ -66,7 +66,8 @@ def test_host_mirror_pipeline_matches_oracle(tmp_path, orc):
         f.write(seeds["nrm"].astype(np.float32).tobytes())
         f.write(seeds["ref"].astype(np.int32).tobytes())
         f.write(struct.pack("<iiii", CELL_SEED, CELL_EXP, MIN_VIS, LEVELS))
-    r = subprocess.run([exe, fin, fout], capture_output=True, text=True)
+    fply = str(tmp_path / "cloud.ply")
+    r = subprocess.run([exe, fin, fout, fply], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert "host mirror ok" in r.stdout
 
@@ -115,3 +116,11 @@ def test_host_mirror_pipeline_matches_oracle(tmp_path, orc):
         for k in ("pos", "nrm", "rgb", "ref", "nvis", "vis"):
             assert np.array_equal(exp[k], want[k]), k
         assert len(want["ref"]) > m.sum() > 0
+        f.read(32)                                               # Expand::Stats
+        cre = _read_patches(f, sc.n_views)                       # Seed::CreatePatchesFromPoints
+    orc.set_homography_mode(0)
+    oc = orc.create_patches(orc.Views(sc.P, sc.images), seeds["pos"].astype(np.float64))
+    for k in ("pos", "nrm", "ref", "nvis", "vis"):
+        assert np.array_equal(cre[k], oc[k]), k
+    ply = open(fply).read().split("\n")
+    assert ply[0] == "ply" and ply[2] == f"element vertex {len(want['ref'])}"
