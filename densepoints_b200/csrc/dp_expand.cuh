@@ -556,7 +556,7 @@ extern "C" int dp_expand_level_local(dp_context *ctx, int cell_size, int rank, i
   if (!n_records) return DP_ERR_INVALID_ARG;
   *n_records = 0;
   DpOrganizer &o = ctx->org;
-  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  cudaStream_t st = (cudaStream_t)stream;  // as given: 0 is the legacy default stream (torch's)
   int64_t fb = 0, fe = 0;
   dp_expand_frontier(ctx, &fb, &fe);
   const long long nf = fe - fb;
@@ -648,7 +648,7 @@ extern "C" int dp_expand_level_commit(dp_context *ctx, const void *records_dev, 
   int rc = org_check(ctx);
   if (rc != DP_OK) return rc;
   DpOrganizer &o = ctx->org;
-  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  cudaStream_t st = (cudaStream_t)stream;  // as given: 0 is the legacy default stream (torch's)
   int64_t fb = 0, fe = 0;
   dp_expand_frontier(ctx, &fb, &fe);
   const long long nf = fe - fb;

@@ -34,6 +34,26 @@ def partition_views(ref, n_views: int, world: int) -> np.ndarray:
     return rov
 
 
+def views_of_rank(n_views: int, rank: int, world: int):
+    """The views rank `rank` renders / loads before share_images: v % world == rank."""
+    return list(range(rank, n_views, world))
+
+
+def share_images(images, rank: int, world: int, device=None):
+    """Every rank loaded (or rendered) only views_of_rank(...); broadcast each image from its
+    owner so that all ranks hold the full, bit-identical image set (views are replicated,
+    SURVEY 8e).  In place; returns the list."""
+    if world <= 1:
+        return images
+    for v in range(len(images)):
+        t = torch.from_numpy(np.ascontiguousarray(images[v]))
+        if device is not None:
+            t = t.to(device)
+        dist.broadcast(t, src=v % world)
+        images[v] = t.cpu().numpy()
+    return images
+
+
 class CudaLevelBackend:
     """The three per-level steps on a dp_context (device records = torch int32 tensors)."""
 

@@ -85,12 +85,18 @@ class Texture3D:
         return out
 
 
-def _render(P_list, centers, Rs, f, cx, cy, width, height, surface, param, tex, chunk=1 << 18):
+def _render(P_list, centers, Rs, f, cx, cy, width, height, surface, param, tex, chunk=1 << 18,
+            only_views=None):
+    """only_views: render just these view ids (the others stay black) -- multi-process drivers
+    render a slice per rank and exchange the images (distributed.share_images)."""
     images = []
     jj, ii = np.meshgrid(np.arange(width, dtype=np.float64), np.arange(height, dtype=np.float64))
     pix = np.stack([(jj.ravel() - cx) / f, (ii.ravel() - cy) / f, np.ones(width * height)], 1)
-    for C0, R in zip(centers, Rs):
+    for vid, (C0, R) in enumerate(zip(centers, Rs)):
         img = np.zeros((height * width, 3), np.uint8)
+        if only_views is not None and vid not in only_views:
+            images.append(img.reshape(height, width, 3))
+            continue
         for s in range(0, pix.shape[0], chunk):
             d = pix[s:s + chunk] @ R          # rows: R^T * pix  (camera -> world)
             if surface == "plane":            # z = 0
@@ -115,7 +121,7 @@ def _render(P_list, centers, Rs, f, cx, cy, width, height, surface, param, tex, 
 
 
 def make_plane_scene(seed=1, n_views=3, width=640, height=480, f=None, distance=20.0,
-                     yaw_spread_deg=15.0, extent=None, name="C1-plane"):
+                     yaw_spread_deg=15.0, extent=None, name="C1-plane", only_views=None):
     """Config C1: textured plane z=0 seen by `n_views` TestScene-style pinholes
     (test_data_generator.cpp:8-13 scaled to the image: f = width/4 * ... ) placed on an
     arc at `distance` with +-yaw_spread around the plane normal."""
@@ -135,13 +141,14 @@ def make_plane_scene(seed=1, n_views=3, width=640, height=480, f=None, distance=
         Ps.append(projection(f, cx, cy, R, c))
     px_world = distance / f
     tex = Texture3D(seed + 1000, (3.0 * px_world, 14.0 * px_world))
-    images = _render(Ps, centers, Rs, f, cx, cy, width, height, "plane", extent, tex)
+    images = _render(Ps, centers, Rs, f, cx, cy, width, height, "plane", extent, tex,
+                     only_views=only_views)
     return Scene(name, np.array(Ps), images, width, height, "plane", extent=extent,
                  centers=np.array(centers))
 
 
 def make_sphere_scene(seed=2, n_views=16, width=1280, height=960, f=1000.0, radius=5.0,
-                      distance=20.0, cap_deg=32.0, name="C2-sphere"):
+                      distance=20.0, cap_deg=32.0, name="C2-sphere", only_views=None):
     """Configs C2/C3: textured sphere, `n_views` cameras on a spherical cap
     (sqrt(n) x sqrt(n) grid of azimuth/elevation within +-cap_deg) looking at the centre."""
     cx, cy = width / 2.0, height / 2.0
@@ -159,7 +166,8 @@ def make_sphere_scene(seed=2, n_views=16, width=1280, height=960, f=1000.0, radi
         Ps.append(projection(f, cx, cy, R, c))
     px_world = (distance - radius) / f
     tex = Texture3D(seed + 1000, (3.0 * px_world, 14.0 * px_world))
-    images = _render(Ps, centers, Rs, f, cx, cy, width, height, "sphere", radius, tex)
+    images = _render(Ps, centers, Rs, f, cx, cy, width, height, "sphere", radius, tex,
+                     only_views=only_views)
     return Scene(name, np.array(Ps), images, width, height, "sphere", radius=radius,
                  centers=np.array(centers))
 

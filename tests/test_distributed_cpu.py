@@ -15,8 +15,9 @@ from densepoints_b200 import scenes
 CELL = 5
 
 
-def _scene():
-    sc = scenes.make_plane_scene(seed=5, n_views=4, width=160, height=120, yaw_spread_deg=14.0)
+def _scene(only_views=None):
+    sc = scenes.make_plane_scene(seed=5, n_views=4, width=160, height=120, yaw_spread_deg=14.0,
+                                 only_views=only_views)
     seeds = scenes.make_seeds(sc, 40, seed=6, depth_noise=0.004, tilt_deg=4.0)
     return sc, seeds
 
@@ -68,7 +69,12 @@ def _worker(rank, world, port, outdir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle import oracle as orc
-    sc, seeds = _scene()
+    # every rank renders its slice of the views, then the images are exchanged
+    sc, seeds = _scene(only_views=dd.views_of_rank(4, rank, world))
+    assert not sc.images[(rank + 1) % world].any()
+    dd.share_images(sc.images, rank, world)
+    full, _ = _scene()
+    assert all(np.array_equal(a, b) for a, b in zip(sc.images, full.images))
     V = orc.Views(sc.P, sc.images)
     prm = orc.default_params(minimum_visible_image=2)
     nvis, vis, _, _ = orc.visibility_batch(V, seeds["pos"], seeds["nrm"], seeds["ref"])

@@ -223,7 +223,7 @@ def test_many_views_multi_round(many_views, exact_orc):
     assert d["nvis"].max() > 32 and (d["nvis"] > 16).mean() > 0.5
     g_nvis, g_vis, _, _ = d["ctx"].visibility(sd["pos"], sd["nrm"], sd["ref"])
     assert np.array_equal(g_nvis, d["nvis"]) and np.array_equal(g_vis, d["vis"])
-    for s in (5, 7):
+    for s in (5, 7, 11, 16):
         ncc, tex, valid = d["ctx"].score(sd["pos"], sd["nrm"], sd["ref"], d["nvis"], d["vis"], s,
                                          want_tex=True)
         o_ncc, o_tex, o_valid = exact_orc.score_batch(d["V"], sd["pos"], sd["nrm"], sd["ref"],
@@ -235,12 +235,13 @@ def test_many_views_multi_round(many_views, exact_orc):
                                                     d["nvis"], d["vis"], s, 0.6, 3)
         assert np.array_equal(keep, o_keep) and np.array_equal(nv, o_nv) and np.array_equal(vi, o_vi)
         assert (nv < d["nvis"]).any() and keep.any()
-    n = 80
-    pos, nrm, ev, xb = d["ctx"].refine(sd["pos"][:n], sd["nrm"][:n], sd["ref"][:n], d["nvis"][:n],
-                                       d["vis"][:n], 5)
-    o_pos, o_nrm, o_ev, o_xb = exact_orc.refine_batch(d["V"], sd["pos"][:n], sd["nrm"][:n],
-                                                      sd["ref"][:n], d["nvis"][:n], d["vis"][:n], 5)
-    assert np.array_equal(ev, o_ev) and np.array_equal(pos, o_pos) and np.array_equal(nrm, o_nrm)
+    for s, n in ((5, 80), (11, 40)):
+        pos, nrm, ev, xb = d["ctx"].refine(sd["pos"][:n], sd["nrm"][:n], sd["ref"][:n],
+                                           d["nvis"][:n], d["vis"][:n], s)
+        o_pos, o_nrm, o_ev, o_xb = exact_orc.refine_batch(d["V"], sd["pos"][:n], sd["nrm"][:n],
+                                                          sd["ref"][:n], d["nvis"][:n],
+                                                          d["vis"][:n], s)
+        assert np.array_equal(ev, o_ev) and np.array_equal(pos, o_pos) and np.array_equal(nrm, o_nrm)
 
 
 def test_large_roi_takes_the_unstaged_path(capi_mod, exact_orc):

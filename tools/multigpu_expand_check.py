@@ -48,8 +48,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     h = a.width * 3 // 4
+    # each rank renders a slice of the views; the images are then exchanged (replicated views)
     sc = scenes.make_plane_scene(seed=4, n_views=a.views, width=a.width, height=h,
-                                 yaw_spread_deg=20.0)
+                                 yaw_spread_deg=20.0,
+                                 only_views=dd.views_of_rank(a.views, rank, world))
+    dd.share_images(sc.images, rank, world, dev)
     seeds = scenes.make_seeds(sc, a.seeds, seed=40, depth_noise=0.003, tilt_deg=4.0)
     ctx = capi.Context(local)
     ctx.set_views(sc.P, sc.images)
