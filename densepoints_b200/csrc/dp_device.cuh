@@ -295,6 +295,10 @@ __device__ __forceinline__ void dp_setup_views(const DpViewDev *__restrict__ vie
 
 // Generic staging: tile rows padded to a power-of-two pitch so the flat index splits with a
 // shift and a mask; each 32-lane step loads 32/pitch whole rows with 32-bit loads.
+#ifndef DP_STAGE_FAST
+#define DP_STAGE_FAST 1
+#endif
+template <int NFAST>
 __device__ __forceinline__ bool dp_stage_roi(const DpViewSetup &R, uint32_t *tile, int tile_cap,
                                              int lane) {
   const int lgp = R.lgp, rw = R.rw, pitch = R.pitch;
@@ -302,18 +306,37 @@ __device__ __forceinline__ bool dp_stage_roi(const DpViewSetup &R, uint32_t *til
   if (area > tile_cap) return false;
   const uint32_t *__restrict__ src = R.src;
   const int cmask = (1 << lgp) - 1;
+#if DP_STAGE_FAST
+  // The first 32*NFAST tile entries (the whole ROI in the normal case) without a branch: all
+  // loads are issued before the first store, lanes past the ROI load nothing and store 0.
+  uint32_t v[NFAST];
+#pragma unroll
+  for (int u = 0; u < NFAST; ++u) {
+    const int t = lane + 32 * u;
+    const int r = t >> lgp, c = t & cmask;
+    v[u] = (t < area && c < rw) ? __ldg(src + (unsigned)(r * pitch + c)) : 0u;
+  }
+#pragma unroll
+  for (int u = 0; u < NFAST; ++u) tile[lane + 32 * u] = v[u];
+  if (area > 32 * NFAST)
+    for (int t = 32 * NFAST + lane; t < area; t += 32) {
+      const int r = t >> lgp, c = t & cmask;
+      if (c < rw) tile[t] = __ldg(src + (unsigned)(r * pitch + c));
+    }
+#else
   for (int t = lane; t < area; t += 32) {
     const int r = t >> lgp, c = t & cmask;
     if (c < rw) tile[t] = __ldg(src + (unsigned)(r * pitch + c));
   }
+#endif
   __syncwarp();
   return true;
 }
 
-template <int NPASS, bool WRITE_TEX>
+template <int NPASS, bool WRITE_TEX, bool staged>
 __device__ __forceinline__ void dp_view_texture(const DpViewSetup &R, int npx,
                                                 const DpTexels<NPASS> &tx, const uint32_t *tile0,
-                                                bool staged, int lane, int (&g)[NPASS],
+                                                int lane, int (&g)[NPASS],
                                                 uint8_t *__restrict__ tex_out) {
   const uint32_t *tile = tile0 + R.xoff;
   const double M0 = R.M[0], M1 = R.M[1], M2 = R.M[2], M3 = R.M[3], M4 = R.M[4], M5 = R.M[5],
@@ -326,6 +349,9 @@ __device__ __forceinline__ void dp_view_texture(const DpViewSetup &R, int npx,
 #pragma unroll
   for (int j = 0; j < NPASS; ++j) {
     const int i = lane + 32 * j;
+#ifdef DP_ABL_ONEPASS  // ablation (wrong results): only the first texel pass is computed
+    if (j > 0) { g[j] = g[0]; continue; }
+#endif
     double x, y;
     tx.get(j, i, x, y);
     const double Wd = fma(M6, x, fma(M7, y, 1.0));
@@ -345,9 +371,10 @@ __device__ __forceinline__ void dp_view_texture(const DpViewSetup &R, int npx,
       p00 = tile[o0 + x0]; p01 = tile[o0 + x1];
       p10 = tile[o1 + x0]; p11 = tile[o1 + x1];
     } else {
-      const uint32_t *r0 = src + (size_t)y0 * pitch, *r1 = src + (size_t)y1 * pitch;
-      p00 = __ldg(r0 + x0); p01 = __ldg(r0 + x1);
-      p10 = __ldg(r1 + x0); p11 = __ldg(r1 + x1);
+      // unsigned 32-bit element offsets from the ROI origin: one IMAD.WIDE.U32 per tap
+      const unsigned o0 = (unsigned)(y0 * pitch), o1 = (unsigned)(y1 * pitch);
+      p00 = __ldg(src + (o0 + (unsigned)x0)); p01 = __ldg(src + (o0 + (unsigned)x1));
+      p10 = __ldg(src + (o1 + (unsigned)x0)); p11 = __ldg(src + (o1 + (unsigned)x1));
     }
     // separable form of the 15-bit weights (32-ax)(32-ay)*32 ...: exact in integers,
     // (sum*32 + 2^14) >> 15 == (sum + 2^9) >> 10.  B and R share one multiply per tap pair
@@ -355,11 +382,12 @@ __device__ __forceinline__ void dp_view_texture(const DpViewSetup &R, int npx,
     const uint32_t wx1 = (uint32_t)axw, wx0 = 32u - wx1, wy1 = (uint32_t)ayw, wy0 = 32u - wy1;
     const uint32_t br0 = (p00 & 0x00ff00ffu) * wx0 + (p01 & 0x00ff00ffu) * wx1;  // B | R<<16
     const uint32_t br1 = (p10 & 0x00ff00ffu) * wx0 + (p11 & 0x00ff00ffu) * wx1;
-    const uint32_t g0 = ((p00 >> 8) & 0xffu) * wx0 + ((p01 >> 8) & 0xffu) * wx1;
-    const uint32_t g1 = ((p10 >> 8) & 0xffu) * wx0 + ((p11 >> 8) & 0xffu) * wx1;
+    // G stays in place (bits 8..15): all its partial sums carry a factor 2^8, <= 26 bits
+    const uint32_t g0 = (p00 & 0xff00u) * wx0 + (p01 & 0xff00u) * wx1;
+    const uint32_t g1 = (p10 & 0xff00u) * wx0 + (p11 & 0xff00u) * wx1;
     const uint32_t B = ((br0 & 0xffffu) * wy0 + (br1 & 0xffffu) * wy1 + 512u) >> 10;
     const uint32_t Rr = ((br0 >> 16) * wy0 + (br1 >> 16) * wy1 + 512u) >> 10;
-    const uint32_t G = (g0 * wy0 + g1 * wy1 + 512u) >> 10;
+    const uint32_t G = (g0 * wy0 + g1 * wy1 + (512u << 8)) >> 18;
     // cv::cvtColor(BGR2GRAY), 8U: 15-bit fixed point
     const int gray = (int)((3735u * B + 19235u * G + 9798u * Rr + (1u << 14)) >> 15);
     g[j] = (i < npx) ? gray : 0;

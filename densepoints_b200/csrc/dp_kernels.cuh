@@ -25,6 +25,11 @@ __host__ __device__ constexpr int dp_score_min_ctas(int npass) {
 #endif
 __host__ __device__ constexpr int dp_refine_min_ctas(int npass) { return npass <= 8 ? DP_RMINCTA : 1; }
 
+// Tuning switches (tools/build_variant.sh).
+#ifndef DP_REFINE_DIRECT
+#define DP_REFINE_DIRECT 1  // refine kernel: no staging, bilinear taps straight from global / L1
+#endif
+
 struct DpPatchArgs {
   const DpViewDev *views;
   int n_views;
@@ -45,18 +50,23 @@ struct DpScoreArgs {
   uint8_t *keep;
 };
 
-// TMA staging is a per-kernel choice (measured on B200, profiles/r01_summary.md): it pays in
-// the scoring / filter kernel (+2 %), not in the refine kernel (-3 %), whose warps are already
-// bound by fixed-latency dependencies rather than by the staging loop.
+// How the texel pass gets its source pixels is a per-kernel choice, measured on B200
+// (profiles/r01_summary.md):
+//  * score / filter kernel (TMA = true): every patch is visited once, nothing is reused, so
+//    the ROI is staged in shared memory -- by TMA when the footprint fits one 16x16 box (up
+//    to 4 texel passes, s <= 11: two 1 KB buffers per warp, the next view's box in flight
+//    while the current one is computed), else by the warp itself into one buffer of kTilePx
+//    pixels (~4x the texel count, for oblique / zoomed views) or, beyond that, not at all.
+//  * refine kernel (TMA = false): consecutive Nelder-Mead evaluations of a patch read almost
+//    the same pixels, 97 % of the loads hit L1, and staging them again for every evaluation
+//    costs more than it saves: the taps are gathered straight from global memory (+16 % over
+//    staging; TMA staging -3 %, cp.async double buffering -1 %, tld4 texture gather +2 %).
 template <int NPASS, bool TMA>
 struct DpTileCfg {
-  // TMA: up to 4 texel passes (s <= 11) the footprint normally fits one 16x16 box: two 1 KB
-  // buffers per warp, the next view's box in flight while the current one is computed.
-  // Otherwise (and for ROIs that do not fit the box) the warp stages the ROI itself into one
-  // buffer of kTilePx pixels (~4x the texel count, for oblique / zoomed views) or, beyond
-  // that, gathers straight from global memory.
   static constexpr bool kTma = TMA && NPASS <= 4;
-  static constexpr int kTilePx = kTma ? DP_TMA_BOX * DP_TMA_BOX : (128 * NPASS < 768 ? 128 * NPASS : 768);
+  static constexpr bool kDirect = !TMA && (DP_REFINE_DIRECT != 0);
+  static constexpr int kTilePx =
+      kDirect ? 1 : (kTma ? DP_TMA_BOX * DP_TMA_BOX : (128 * NPASS < 768 ? 128 * NPASS : 768));
   static constexpr int kBufs = kTma ? 2 : 1;
 };
 
@@ -107,7 +117,14 @@ __device__ __forceinline__ void dp_eval_views(const DpViewDev *__restrict__ view
   for (int k0 = 0; k0 < nv; k0 += DP_ROUND) {
     const int kc = min(DP_ROUND, nv - k0);
     __syncwarp();
+#ifdef DP_ABL_NOSETUP  // ablation (wrong results): set-up only once per patch
+    if (!(phase & 0x80000000u)) {
+      dp_setup_views(views, n_views, vis + k0, kc, s, f, recs, lane, kTma);
+      phase |= 0x80000000u;
+    }
+#else
     dp_setup_views(views, n_views, vis + k0, kc, s, f, recs, lane, kTma);
+#endif
     __syncwarp();
     if (kTma && lane == 0 && recs[0].ok && recs[0].tmap != nullptr)  // first box of the round
       dp_tma_load_tile(ws.tile[0], recs[0].tmap, recs[0].tlx, recs[0].tly, &ws.bar[0]);
@@ -127,18 +144,26 @@ __device__ __forceinline__ void dp_eval_views(const DpViewDev *__restrict__ view
       unsigned s1 = 0, s2 = 0;
       double num = 0.0;
       if (ok) {
-        bool staged;
+        bool staged = false;
         if (kTma && R.tmap != nullptr) {
           dp_mbar_wait(&ws.bar[b], (phase >> b) & 1u);
           phase ^= 1u << b;
           staged = true;
-        } else {
-          staged = dp_stage_roi(R, ws.tile[b], DpTileCfg<NPASS, TMA>::kTilePx, lane);
+        } else if (!DpTileCfg<NPASS, TMA>::kDirect) {
+#ifdef DP_ABL_NOSTAGE  // ablation (wrong results): texels read whatever the tile holds
+          staged = true;
+#else
+          staged = dp_stage_roi<(NPASS < 4 ? NPASS : 4)>(R, ws.tile[b],
+                                                         DpTileCfg<NPASS, TMA>::kTilePx, lane);
+#endif
         }
         int g[NPASS];
-        dp_view_texture<NPASS, WRITE_TEX>(R, npx, tx, ws.tile[b], staged, lane, g,
-                                          WRITE_TEX ? tex_base + (size_t)(k0 + l) * npx * 3
-                                                    : nullptr);
+        uint8_t *tex_out = WRITE_TEX ? tex_base + (size_t)(k0 + l) * npx * 3 : nullptr;
+        // two instantiations, so neither texel loop carries the other's addressing
+        if (staged)
+          dp_view_texture<NPASS, WRITE_TEX, true>(R, npx, tx, ws.tile[b], lane, g, tex_out);
+        else
+          dp_view_texture<NPASS, WRITE_TEX, false>(R, npx, tx, ws.tile[b], lane, g, tex_out);
         dp_moments<NPASS>(g, s1, s2);
         if (k0 + l == 0) {
           a1 = s1;
@@ -379,6 +404,9 @@ __global__ void __launch_bounds__(DP_RWARPS * 32, dp_refine_min_ctas(NPASS)) dp_
       if (a.evals && lane == 0) a.evals[i] = 0;
       continue;
     }
+#ifdef DP_ABL_NOSETUP
+    phase = 0;
+#endif
     const int nv = min(a.p.nvis[i], a.p.vstride);
     const int ref = a.p.ref[i];
     const bool ref_ok = ref >= 0 && ref < a.p.n_views;
