@@ -11,6 +11,7 @@
 #include "dp_aux_kernels.cuh"
 #include "dp_context.h"
 #include "dp_kernels.cuh"
+#include "dp_group.cuh"
 
 // ---------------------------------------------------------------------------------------
 // helpers
@@ -252,7 +253,9 @@ extern "C" int dp_upload_view(dp_context *ctx, int view_id, const double P[12], 
   l.width = width;
   l.height = height;
   l.pitch_px = (width + 31) & ~31;  // 128-byte aligned rows
-  DP_CUDA(ctx, cudaMalloc(&l.img, (size_t)l.pitch_px * height * sizeof(uint32_t)));
+  // one spare row: the texel pass may read (never use) the right / lower neighbour of an edge pixel
+  DP_CUDA(ctx, cudaMalloc(&l.img, (size_t)l.pitch_px * (height + 1) * sizeof(uint32_t)));
+  DP_CUDA(ctx, cudaMemsetAsync(l.img + (size_t)l.pitch_px * height, 0, (size_t)l.pitch_px * 4, ctx->stream));
   dp_encode_tmap(l);
   v.levels.push_back(l);
   const size_t bytes = stride * (size_t)height;
@@ -436,6 +439,23 @@ static cudaError_t launch_refine(const DpRefineArgs &a, int sm_count, cudaStream
   return cudaGetLastError();
 }
 
+#ifndef DP_REFINE_GROUP
+#define DP_REFINE_GROUP 1  // cells up to 8x8: four patches per warp (dp_group.cuh)
+#endif
+template <int NP>
+static cudaError_t launch_refine_group(const DpRefineArgs &a, int sm_count, cudaStream_t st) {
+  int per_sm = 1;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dp_refine_group_kernel<NP>,
+                                                                DP_RWARPS * 32, 0);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  const long long per_cta = (long long)DP_RWARPS * DP_GROUPS;
+  long long want = ((long long)a.p.n + per_cta - 1) / per_cta;
+  long long grid = std::min<long long>(want, (long long)sm_count * per_sm);
+  dp_refine_group_kernel<NP><<<(unsigned)grid, DP_RWARPS * 32, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
 extern "C" int dp_refine_dev(dp_context *ctx, dp_patch_dev *p, int cell_size, const uint8_t *mask,
                              int32_t *evals, double *xbest, void *stream) {
   int rc = check_patch_dev(ctx, p, cell_size);
@@ -469,6 +489,14 @@ extern "C" int dp_refine_dev(dp_context *ctx, dp_patch_dev *p, int cell_size, co
     a.order = order;
   }
   cudaError_t e;
+  if (DP_REFINE_GROUP && cell_size <= 8) {
+#define DP_GCASE(S) case S: e = launch_refine_group<(S * S + DP_GL - 1) / DP_GL>(a, ctx->sm_count, st); break
+    switch (cell_size) {  // texel passes of a group = ceil(s^2 / DP_GL)
+      DP_GCASE(2); DP_GCASE(3); DP_GCASE(4); DP_GCASE(5); DP_GCASE(6); DP_GCASE(7);
+      default: e = launch_refine_group<(64 + DP_GL - 1) / DP_GL>(a, ctx->sm_count, st); break;
+    }
+#undef DP_GCASE
+  } else
   switch (npass_for(cell_size)) {
     case 1: e = launch_refine<1>(a, ctx->sm_count, st); break;
     case 2: e = launch_refine<2>(a, ctx->sm_count, st); break;

@@ -205,11 +205,16 @@ __device__ __forceinline__ void dp_mbar_wait(uint64_t *bar, unsigned parity) {
 
 #define DP_ROUND 16  // views whose set-up records are resident at once (per warp)
 
+// GL = lanes that share one patch (32: the whole warp; 8: four patches per warp, each group of
+// 8 lanes sets up GL/4 views of its own patch per pass and writes to its own `recs`).  kcount
+// is this group's number of views in the round, kcmax the largest kcount in the warp (the loop
+// bound must be warp-uniform: the shuffles below are full-warp).
+template <int GL = 32>
 __device__ __forceinline__ void dp_setup_views(const DpViewDev *__restrict__ views, int n_views,
-                                               const int32_t *vis, int kcount, int s,
+                                               const int32_t *vis, int kcount, int kcmax, int s,
                                                const DpFrame &f, DpViewSetup *recs, int lane,
                                                bool use_tma) {
-  const int c = lane & 3, slot = lane >> 2;
+  const int c = lane & 3, slot = (lane & (GL - 1)) >> 2;
   const double sgx = (c == 1 || c == 2) ? 1.0 : -1.0;  // corners (-,-) (+,-) (+,+) (-,+),
   const double sgy = (c >= 2) ? 1.0 : -1.0;            // patch.cpp:119-123
   const double X0 = xadd(xadd(f.p[0], sgx * f.ax[0]), sgy * f.ay[0]);
@@ -217,7 +222,7 @@ __device__ __forceinline__ void dp_setup_views(const DpViewDev *__restrict__ vie
   const double X2 = xadd(xadd(f.p[2], sgx * f.ax[2]), sgy * f.ay[2]);
   const double inv_s = 1.0 / (double)s;
 #pragma unroll 1
-  for (int base = 0; base < kcount; base += 8) {
+  for (int base = 0; base < kcmax; base += GL / 4) {
     const int k = base + slot;
     const bool active = k < kcount;
     const int vid = active ? vis[k] : -1;
@@ -333,22 +338,23 @@ __device__ __forceinline__ bool dp_stage_roi(const DpViewSetup &R, uint32_t *til
   return true;
 }
 
-template <int NPASS, bool WRITE_TEX, bool staged>
-__device__ __forceinline__ void dp_view_texture(const DpViewSetup &R, int npx,
-                                                const DpTexels<NPASS> &tx, const uint32_t *tile0,
-                                                int lane, int (&g)[NPASS],
+// `lane` is the lane's index inside its group of GL lanes; it owns texels lane + GL*j.
+template <int NPASS, bool WRITE_TEX, bool staged, int GL = 32, typename TX = DpTexels<NPASS>>
+__device__ __forceinline__ void dp_view_texture(const DpViewSetup &R, int npx, const TX &tx,
+                                                const uint32_t *tile0, int lane, int (&g)[NPASS],
                                                 uint8_t *__restrict__ tex_out) {
   const uint32_t *tile = tile0 + R.xoff;
   const double M0 = R.M[0], M1 = R.M[1], M2 = R.M[2], M3 = R.M[3], M4 = R.M[4], M5 = R.M[5],
                M6 = R.M[6], M7 = R.M[7];
   const uint32_t *__restrict__ src = R.src;
-  const int pitch = R.pitch, rw = R.rw, rh = R.rh, lgp = R.lgp;
+  const int pitch = R.pitch, lgp = R.lgp;
+  const int xmax = (R.rw - 1) << 5, ymax = (R.rh - 1) << 5;
   // ---- warp the texel grid ------------------------------------------------------------------
   // Branch-free: lanes past the last texel compute on a clamped (harmless) coordinate and are
   // masked at the end, so the NPASS independent passes can be interleaved by the scheduler.
 #pragma unroll
   for (int j = 0; j < NPASS; ++j) {
-    const int i = lane + 32 * j;
+    const int i = lane + GL * j;
 #ifdef DP_ABL_ONEPASS  // ablation (wrong results): only the first texel pass is computed
     if (j > 0) { g[j] = g[0]; continue; }
 #endif
@@ -361,20 +367,25 @@ __device__ __forceinline__ void dp_view_texture(const DpViewSetup &R, int npx,
     const double fY = fma(M3, x, fma(M4, y, M5)) * r;
     const int Xi = __double2int_rn(fX);  // saturate_cast<int>(cvRound), half to even
     const int Yi = __double2int_rn(fY);
-    const int sx = Xi >> 5, axw = Xi & 31;  // INTER_BITS = 5
-    const int sy = Yi >> 5, ayw = Yi & 31;
-    const int x0 = min(max(sx, 0), rw - 1), x1 = min(max(sx + 1, 0), rw - 1);  // BORDER_REPLICATE
-    const int y0 = min(max(sy, 0), rh - 1), y1 = min(max(sy + 1, 0), rh - 1);  // at the ROI edge
+    // BORDER_REPLICATE at the ROI edge: a clamped tap pair reads the same pixel twice, so the
+    // result is that pixel whatever the weight.  Clamping the 1/32-px coordinate itself to
+    // [0, 32 (rw-1)] gives the same blend -- inside nothing changes, outside the coordinate
+    // lands exactly on the edge pixel with weight 0 for its right / lower neighbour -- and the
+    // taps are simply (x0, y0) + {0,1}^2.  The neighbour of an edge pixel may lie outside the
+    // ROI (never outside the allocation: images carry one spare row); its weight is 0.
+    const int Xc = min(max(Xi, 0), xmax), Yc = min(max(Yi, 0), ymax);
+    const int x0 = Xc >> 5, axw = Xc & 31;  // INTER_BITS = 5
+    const int y0 = Yc >> 5, ayw = Yc & 31;
     uint32_t p00, p01, p10, p11;
     if (staged) {
-      const int o0 = y0 << lgp, o1 = y1 << lgp;
-      p00 = tile[o0 + x0]; p01 = tile[o0 + x1];
-      p10 = tile[o1 + x0]; p11 = tile[o1 + x1];
+      const uint32_t *t0 = tile + ((y0 << lgp) + x0), *t1 = t0 + (1 << lgp);
+      p00 = t0[0]; p01 = t0[1];
+      p10 = t1[0]; p11 = t1[1];
     } else {
-      // unsigned 32-bit element offsets from the ROI origin: one IMAD.WIDE.U32 per tap
-      const unsigned o0 = (unsigned)(y0 * pitch), o1 = (unsigned)(y1 * pitch);
-      p00 = __ldg(src + (o0 + (unsigned)x0)); p01 = __ldg(src + (o0 + (unsigned)x1));
-      p10 = __ldg(src + (o1 + (unsigned)x0)); p11 = __ldg(src + (o1 + (unsigned)x1));
+      // unsigned 32-bit element offset from the ROI origin: one IMAD.WIDE.U32 per row
+      const uint32_t *r0 = src + (unsigned)(y0 * pitch + x0), *r1 = r0 + pitch;
+      p00 = __ldg(r0); p01 = __ldg(r0 + 1);
+      p10 = __ldg(r1); p11 = __ldg(r1 + 1);
     }
     // separable form of the 15-bit weights (32-ax)(32-ay)*32 ...: exact in integers,
     // (sum*32 + 2^14) >> 15 == (sum + 2^9) >> 10.  B and R share one multiply per tap pair

@@ -1,0 +1,438 @@
+// dp_group.cuh -- refine kernel for small cells (s <= 8): FOUR patches per warp.
+//
+// With one warp per patch (dp_refine_kernel) more than half of the warp instructions of an
+// objective evaluation are not texel work: UnparametrizePatch, the patch frame and the
+// Nelder-Mead state machine are scalar (all 32 lanes compute the same value), the per-view
+// set-up fills 8 lane slots of which ~5 are used, the reductions run over 32 lanes for 49
+// texels, and the texel passes themselves use 49 of 64 lane slots.  Here a patch owns a group
+// of DP_GL = 8 lanes and a warp advances four patches in lockstep:
+//   * scalar work is done once per instruction for four patches;
+//   * the set-up pass handles 2 views of each of the 4 patches (8 slots, all used);
+//   * a 7x7 texture takes 7 passes of 8 lanes (56 slots for 49 texels instead of 64);
+//   * reductions are 3-step shuffle trees inside the group.
+// The warp's control flow stays uniform: every iteration of the main loop is one objective
+// evaluation for each of the four patches (at its own simplex point), the view loop runs to
+// the largest view count in the warp (patches are handed out sorted by view count, so the
+// four usually agree), and only the short Nelder-Mead bookkeeping diverges per group.  A group
+// whose patch has converged writes it back and takes the next patch from the work counter.
+//
+// The arithmetic is the one of dp_kernels.cuh / dp_device.cuh (same functions); only the
+// order of the fp64 partial sums of the NCC numerator differs (8-lane tree), ~1e-16.
+#pragma once
+#include "dp_kernels.cuh"
+
+#ifndef DP_GL
+#define DP_GL 4                  // lanes per patch (measured: 4 > 8 > 16 on B200 at s = 7)
+#endif
+#define DP_GROUPS (32 / DP_GL)   // patches per warp
+#define DP_GROUND DP_GL          // views per round of a group: one per lane in phase C
+
+struct DpGroupLane {
+  int sub;         // lane index inside the group
+  int base;        // first lane of the group
+  unsigned mask;   // the group's lanes
+  bool leader;     // sub == 0
+};
+
+// texel coordinates (x, y) as doubles, from a per-CTA table in shared memory: texel
+// sub + DP_GL*j of the lane is one LDS.128 at a constant offset from the lane's base pointer
+struct DpTexelTable {
+  const double2 *t;  // table + sub
+  __device__ __forceinline__ void get(int j, int, double &xo, double &yo) const {
+    const double2 v = t[DP_GL * j];
+    xo = v.x;
+    yo = v.y;
+  }
+};
+
+template <typename T>
+__device__ __forceinline__ T dp_group_sum(T v, unsigned mask) {
+#pragma unroll
+  for (int o = DP_GL / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+  return v;
+}
+
+// ---- Nelder-Mead helpers, group flavour (state of the group's patch in shared memory, all
+// lanes of the group compute, the leader writes between two group barriers) ---------------
+__device__ __forceinline__ void nmg_store3(double *dst, const double v[3], const DpGroupLane &L) {
+  __syncwarp(L.mask);
+  if (L.leader) { dst[0] = v[0]; dst[1] = v[1]; dst[2] = v[2]; }
+  __syncwarp(L.mask);
+}
+__device__ __forceinline__ void nmg_coord_sum(DpNelderMead &S, const DpGroupLane &L) {
+  double t[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+    t[j] = xadd(xadd(xadd(xadd(0.0, S.P[0][j]), S.P[1][j]), S.P[2][j]), S.P[3][j]);
+  nmg_store3(S.cs, t, L);
+}
+__device__ __forceinline__ void nmg_try_point(DpNelderMead &S, const DpGroupLane &L, int ihi,
+                                              double alpha_) {
+  const double al = (1.0 - alpha_) / 3.0;
+  const double be = xsub(al, alpha_);
+  double pt[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) pt[j] = xsub(xmul(S.cs[j], al), xmul(S.P[ihi][j], be));
+  nmg_store3(S.pt, pt, L);
+}
+__device__ __forceinline__ void nmg_replace(DpNelderMead &S, const DpGroupLane &L, int ihi,
+                                            const double q[3], double yq) {
+  __syncwarp(L.mask);
+  if (L.leader) {
+    S.P[ihi][0] = q[0]; S.P[ihi][1] = q[1]; S.P[ihi][2] = q[2];
+    S.y[ihi] = yq;
+  }
+  __syncwarp(L.mask);
+  nmg_coord_sum(S, L);
+}
+__device__ __forceinline__ void nmg_shrink_vertex(DpNelderMead &S, const DpGroupLane &L, int idx,
+                                                  int ilo) {
+  double pt[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) pt[j] = xmul(0.5, xadd(S.P[idx][j], S.P[ilo][j]));
+  __syncwarp(L.mask);
+  if (L.leader) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { S.P[idx][j] = pt[j]; S.pt[j] = pt[j]; }
+  }
+  __syncwarp(L.mask);
+}
+
+enum { NMG_INIT, NMG_REFLECT, NMG_EXPAND, NMG_CONTRACT, NMG_SHRINK };
+
+// One step of cv::DownhillSolver's state machine (the same decision tree as in
+// dp_refine_kernel): consumes the objective value of S.pt, leaves the next point to
+// evaluate in S.pt; returns true when the solver stops (S.pt = best vertex).
+__device__ __forceinline__ bool nmg_step(DpNelderMead &S, const DpGroupLane &L, int &state, int &idx,
+                                         int &fcount, int &ilo, int &ihi, double fval, double eps,
+                                         int max_evals) {
+  bool decide = false;
+  if (state == NMG_INIT) {
+    __syncwarp(L.mask);
+    if (L.leader) S.y[idx] = fval;
+    __syncwarp(L.mask);
+    if (++idx < 4) {
+      const double q[3] = {S.P[idx][0], S.P[idx][1], S.P[idx][2]};
+      nmg_store3(S.pt, q, L);
+    } else {
+      nmg_coord_sum(S, L);
+      decide = true;
+    }
+  } else if (state == NMG_REFLECT) {
+    const double q[3] = {S.pt[0], S.pt[1], S.pt[2]};
+    const double y_lo = S.y_lo, y_nhi = S.y_nhi;
+    __syncwarp(L.mask);
+    if (L.leader) {
+      S.pa[0] = q[0]; S.pa[1] = q[1]; S.pa[2] = q[2];
+      S.y_alpha = fval;
+    }
+    __syncwarp(L.mask);
+    if (fval < y_nhi) {
+      if (fval < y_lo) {  // better than the best: try twice as far
+        state = NMG_EXPAND;
+        nmg_try_point(S, L, ihi, -2.0);
+        ++fcount;
+      } else {
+        nmg_replace(S, L, ihi, q, fval);  // replacePoint(alpha = -1)
+        decide = true;
+      }
+    } else {
+      state = NMG_CONTRACT;
+      nmg_try_point(S, L, ihi, 0.5);
+      ++fcount;
+    }
+  } else if (state == NMG_EXPAND) {
+    const double y_alpha = S.y_alpha;
+    const bool better = fval < y_alpha;
+    const double q[3] = {better ? S.pt[0] : S.pa[0], better ? S.pt[1] : S.pa[1],
+                         better ? S.pt[2] : S.pa[2]};
+    nmg_replace(S, L, ihi, q, better ? fval : y_alpha);
+    decide = true;
+  } else if (state == NMG_CONTRACT) {
+    if (fval < S.y_hi) {
+      const double q[3] = {S.pt[0], S.pt[1], S.pt[2]};
+      nmg_replace(S, L, ihi, q, fval);
+      decide = true;
+    } else {  // shrink every vertex but the best halfway towards it
+      state = NMG_SHRINK;
+      idx = (ilo == 0) ? 1 : 0;
+      nmg_shrink_vertex(S, L, idx, ilo);
+    }
+  } else {  // NMG_SHRINK
+    __syncwarp(L.mask);
+    if (L.leader) S.y[idx] = fval;
+    __syncwarp(L.mask);
+    ++idx;
+    if (idx == ilo) ++idx;
+    if (idx < 4) {
+      nmg_shrink_vertex(S, L, idx, ilo);
+    } else {
+      fcount += 3;
+      nmg_coord_sum(S, L);
+      decide = true;
+    }
+  }
+  if (!decide) return false;
+  // ---- find worst, next-to-worst and best vertices; stop test ----------------------------
+  const double yv[4] = {S.y[0], S.y[1], S.y[2], S.y[3]};
+  int inhi;
+  double ylo = yv[0], yhi, ynhi;
+  ilo = 0;
+  if (yv[0] > yv[1]) { ihi = 0; yhi = yv[0]; inhi = 1; ynhi = yv[1]; }
+  else { ihi = 1; yhi = yv[1]; inhi = 0; ynhi = yv[0]; }
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const double yc = yv[v];
+    if (yc <= ylo) { ilo = v; ylo = yc; }
+    if (yc > yhi) { inhi = ihi; ynhi = yhi; ihi = v; yhi = yc; }
+    else if (yc > ynhi && v != ihi) { inhi = v; ynhi = yc; }
+  }
+  if (ilo == inhi || ilo == ihi) {
+#pragma unroll
+    for (int v = 3; v >= 0; --v)  // ascending search, first match wins
+      if (yv[v] == ylo && v != ihi && v != inhi) ilo = v;
+  }
+  const double error = fabs(xsub(yhi, ylo));
+  double range = 0.0;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    double mn = S.P[0][j], mx = S.P[0][j];
+#pragma unroll
+    for (int v = 1; v < 4; ++v) { mn = fmin(mn, S.P[v][j]); mx = fmax(mx, S.P[v][j]); }
+    range = fmax(range, fabs(xsub(mx, mn)));
+  }
+  if (range <= eps || error <= eps || fcount >= max_evals) {
+    const double q[3] = {S.P[ilo][0], S.P[ilo][1], S.P[ilo][2]};
+    nmg_store3(S.pt, q, L);  // best vertex -> x
+    return true;
+  }
+  __syncwarp(L.mask);
+  if (L.leader) { S.y_lo = ylo; S.y_nhi = ynhi; S.y_hi = yhi; }
+  __syncwarp(L.mask);
+  state = NMG_REFLECT;  // reflect the worst point about the centroid of the others
+  nmg_try_point(S, L, ihi, -1.0);
+  ++fcount;
+  return false;
+}
+
+// Optimization::UnparametrizePatch (optimization.cpp:78-96); the group's lanes 0 and 1 compute
+// the sincos of roll and pitch.  `mask` must cover every lane that executes the call.
+__device__ __forceinline__ void dp_unparametrize_g(const double C[3], const double n0[3],
+                                                   const double p0[3], double depth, double roll,
+                                                   double pitch, double n[3], double p[3],
+                                                   const DpGroupLane &L, unsigned mask) {
+  const double k = xadd(1.0, depth);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) p[j] = xadd(C[j], xmul(k, xsub(p0[j], C[j])));
+  double sv, cv;
+  sincos((L.sub & 1) ? pitch : roll, &sv, &cv);
+  const double sa = __shfl_sync(mask, sv, L.base), ca = __shfl_sync(mask, cv, L.base);
+  const double sb = __shfl_sync(mask, sv, L.base + 1), cb = __shfl_sync(mask, cv, L.base + 1);
+  n[0] = xadd(xmul(cb, n0[0]), xmul(-sb, n0[2]));
+  n[1] = xadd(xadd(xmul(xmul(sa, sb), n0[0]), xmul(ca, n0[1])), xmul(xmul(cb, sa), n0[2]));
+  n[2] = xadd(xadd(xmul(xmul(ca, sb), n0[0]), xmul(-sa, n0[1])), xmul(xmul(ca, cb), n0[2]));
+}
+
+// PatchOptimizationOpenCVFunctor::calc for the four patches of the warp at once: mean of
+// (1 - NCC) over the visible views in view order (optimization_opencv.cpp:17-35).  nv = 0
+// marks a group that does not evaluate (no patch, < 2 views, bad reference image).
+// Must be called by the whole warp.
+template <int NP>
+__device__ __forceinline__ double dp_objective_g(const DpViewDev *__restrict__ views, int n_views,
+                                                 int ref, const int32_t *vis, int nv, int s, int npx,
+                                                 const double n[3], const double p[3],
+                                                 DpViewSetup *recs, const DpTexelTable &tx, int lane,
+                                                 const DpGroupLane &L) {
+  DpFrame f;
+  dp_make_frame(views + ref, s, n, p, f);
+  if (nv == 0) f.ok = false;
+  const double scale = 1.0 / (double)npx;  // cv::meanStdDev: mean = sum * (1/N)
+  float da[NP];                             // centred anchor texels (texture 0)
+  unsigned a1 = 0, a2 = 0;
+  bool a_ok = false;
+  double sum = 0.0;
+  const int nvmax = __reduce_max_sync(DP_FULL, nv);
+#pragma unroll 1
+  for (int k0 = 0; k0 < nvmax; k0 += DP_GROUND) {
+    const int kc = min(max(nv - k0, 0), DP_GROUND);   // this group's views in the round
+    const int kcmax = min(DP_GROUND, nvmax - k0);     // warp-uniform loop bound
+    __syncwarp();
+    dp_setup_views<DP_GL>(views, n_views, vis + k0, kc, kcmax, s, f, recs, lane, false);
+    __syncwarp();
+    unsigned my1 = 0, my2 = 0;
+    double mynum = 0.0;
+    int myok = 0;
+#pragma unroll 1
+    for (int l = 0; l < kcmax; ++l) {
+      const DpViewSetup &R = recs[l];
+      const bool ok = l < kc && R.ok != 0;  // uniform inside the group
+      unsigned s1 = 0, s2 = 0;
+      double num = 0.0;
+      if (ok) {
+        int g[NP];
+        dp_view_texture<NP, false, false, DP_GL, DpTexelTable>(R, npx, tx, nullptr, L.sub, g, nullptr);
+        unsigned ma = 0, mb = 0;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+          ma += (unsigned)g[j];
+          mb += (unsigned)(g[j] * g[j]);
+        }
+        s1 = dp_group_sum(ma, L.mask);  // exact integer moments (cv::meanStdDev's sums)
+        s2 = dp_group_sum(mb, L.mask);
+        // fl32(g_i - fl32(mean)): `Mat - scalar` on CV_32F (error_measurements.cpp:54)
+        const float mf = (float)xmul((double)s1, scale);
+        if (k0 + l == 0) {
+          a1 = s1;
+          a2 = s2;
+          a_ok = true;
+#pragma unroll
+          for (int j = 0; j < NP; ++j)
+            da[j] = (L.sub + DP_GL * j < npx) ? __fsub_rn((float)g[j], mf) : 0.f;
+        } else if (a_ok) {
+#pragma unroll
+          for (int j = 0; j < NP; ++j) {
+            const float db = (L.sub + DP_GL * j < npx) ? __fsub_rn((float)g[j], mf) : 0.f;
+            num = xadd(num, xmul((double)da[j], (double)db));
+          }
+          num = dp_group_sum(num, L.mask);
+        }
+      }
+      if (L.sub == l) {
+        my1 = s1;
+        my2 = s2;
+        mynum = num;
+        myok = ok ? 1 : 0;
+      }
+    }
+    // phase C, one view per lane of the group
+    double score = -1.0;  // empty texture (error_measurements.cpp:38-40)
+    if (L.sub < kc && k0 + L.sub >= 1 && myok && a_ok)
+      score = dp_ncc_finish(a1, a2, my1, my2, mynum, scale, npx);
+    // std::accumulate of (1 - NCC) in view order (optimization_opencv.cpp:24, 34)
+    const double term = xsub(1.0, score);
+    for (int l = (k0 == 0 ? 1 : 0); l < kcmax; ++l) {
+      const double t = __shfl_sync(DP_FULL, term, L.base + l);
+      if (l < kc) sum = xadd(sum, t);
+    }
+  }
+  return nv >= 2 ? sum / (double)(nv - 1) : 2.0;  // scores.size() == 0 -> 2
+}
+
+template <int NP>
+__global__ void __launch_bounds__(DP_RWARPS * 32, DP_RMINCTA) dp_refine_group_kernel(DpRefineArgs a) {
+  __shared__ DpViewSetup recs_s[DP_RWARPS][DP_GROUPS][DP_GROUND];
+  __shared__ DpNelderMead nm_s[DP_RWARPS][DP_GROUPS];
+  __shared__ double2 txy_s[NP * DP_GL];
+  const int s = a.p.s, npx = s * s;
+  for (int t = threadIdx.x; t < NP * DP_GL; t += blockDim.x) {
+    const int tt = t < npx ? t : 0;  // lanes past the last texel work on texel 0, masked later
+    const int yy = tt / s;
+    txy_s[t] = make_double2((double)(tt - yy * s), (double)yy);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  DpGroupLane L;
+  L.sub = lane & (DP_GL - 1);
+  L.base = lane & ~(DP_GL - 1);
+  L.mask = ((1u << DP_GL) - 1u) << L.base;
+  L.leader = L.sub == 0;
+  const int grp = lane / DP_GL;
+  DpViewSetup *recs = recs_s[warp][grp];
+  DpNelderMead &S = nm_s[warp][grp];
+  if (L.leader) {  // defined values for the lockstep evaluations of a group without a patch
+    double *z = reinterpret_cast<double *>(&S);
+    for (int j = 0; j < (int)(sizeof(DpNelderMead) / sizeof(double)); ++j) z[j] = 0.0;
+  }
+  __syncthreads();
+  DpTexelTable tx;
+  tx.t = txy_s + L.sub;
+  bool have = false, exhausted = false;
+  long long i = 0;
+  int nv = 0, ref = 0;
+  bool ref_ok = false;
+  const int32_t *vis = a.p.vis;
+  int state = NMG_INIT, idx = 0, fcount = 4, ilo = 0, ihi = 0;
+#pragma unroll 1
+  for (;;) {
+    // ---- 1. a group without a patch takes the next one from the work counter ----------------
+    if (!have && !exhausted) {
+      for (;;) {
+        unsigned int iu = 0;
+        if (L.leader) iu = atomicAdd(a.work_counter, 1u);
+        iu = __shfl_sync(L.mask, iu, L.base);
+        if (iu >= (unsigned int)a.p.n) {
+          exhausted = true;
+          break;
+        }
+        i = a.order ? (long long)a.order[iu] : (long long)iu;
+        if (a.mask != nullptr && a.mask[i] == 0) {  // removed by Seed::RemovePatches
+          if (a.evals && L.leader) a.evals[i] = 0;
+          continue;
+        }
+        nv = min(a.p.nvis[i], a.p.vstride);
+        ref = a.p.ref[i];
+        ref_ok = ref >= 0 && ref < a.p.n_views;
+        vis = a.p.vis + (size_t)i * a.p.vstride;
+        __syncwarp(L.mask);
+        if (L.leader) {
+          // createInitialSimplex: v_i = x0 + step_{i-1}/2 e_{i-1}, then v_0 = x0 - step/2; x0 = 0
+          const double *C = a.p.views[ref_ok ? ref : 0].center;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const double h = xmul(0.5, a.step[j]);
+            S.P[0][j] = xsub(0.0, h);
+            S.pt[j] = xsub(0.0, h);
+#pragma unroll
+            for (int v = 1; v < 4; ++v) S.P[v][j] = (v - 1 == j) ? xadd(0.0, h) : 0.0;
+            S.n0[j] = (double)a.p.nrm[3 * i + j];
+            S.p0[j] = (double)a.p.pos[3 * i + j];
+            S.c3[j] = C[j];
+          }
+        }
+        __syncwarp(L.mask);
+        state = NMG_INIT;
+        idx = 0;
+        fcount = 4;
+        ilo = ihi = 0;
+        have = true;
+        break;
+      }
+    }
+    __syncwarp();
+    if (!__any_sync(DP_FULL, have)) break;
+    // ---- 2. one objective evaluation per group, in lockstep ---------------------------------
+    double n[3], p[3];
+    {
+      const double c3[3] = {S.c3[0], S.c3[1], S.c3[2]};
+      const double n0[3] = {S.n0[0], S.n0[1], S.n0[2]};
+      const double p0[3] = {S.p0[0], S.p0[1], S.p0[2]};
+      dp_unparametrize_g(c3, n0, p0, S.pt[0], S.pt[1], S.pt[2], n, p, L, DP_FULL);
+    }
+    const int nv_eval = (have && nv >= 2 && ref_ok) ? nv : 0;
+    const double fobj = dp_objective_g<NP>(a.p.views, a.p.n_views, ref_ok ? ref : 0, vis, nv_eval, s,
+                                           npx, n, p, recs, tx, lane, L);
+    const double fval = nv_eval ? fobj : 2.0;  // scores.size() == 0 (optimization_opencv.cpp:30-32)
+    // ---- 3. Nelder-Mead bookkeeping of each group (diverges by solver state, short) ---------
+    if (have) {
+      if (nmg_step(S, L, state, idx, fcount, ilo, ihi, fval, a.eps, a.max_evals)) {
+        // best vertex -> one more trip through UnparametrizePatch, then write back;
+        // SetNormal / SetPosition store fp32 (patch.h:38-53)
+        const double c3[3] = {S.c3[0], S.c3[1], S.c3[2]};
+        const double n0[3] = {S.n0[0], S.n0[1], S.n0[2]};
+        const double p0[3] = {S.p0[0], S.p0[1], S.p0[2]};
+        double nb[3], pb[3];
+        dp_unparametrize_g(c3, n0, p0, S.pt[0], S.pt[1], S.pt[2], nb, pb, L, L.mask);
+        if (L.sub < 3) {
+          const double nv_ = L.sub == 0 ? nb[0] : (L.sub == 1 ? nb[1] : nb[2]);
+          const double pv_ = L.sub == 0 ? pb[0] : (L.sub == 1 ? pb[1] : pb[2]);
+          if (ref_ok) {
+            a.p.nrm[3 * i + L.sub] = (float)nv_;
+            a.p.pos[3 * i + L.sub] = (float)pv_;
+          }
+          if (a.xbest) a.xbest[3 * i + L.sub] = S.pt[L.sub];
+        }
+        if (a.evals && L.leader) a.evals[i] = fcount;
+        have = false;
+      }
+    }
+  }
+}

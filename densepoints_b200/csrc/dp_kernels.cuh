@@ -119,11 +119,11 @@ __device__ __forceinline__ void dp_eval_views(const DpViewDev *__restrict__ view
     __syncwarp();
 #ifdef DP_ABL_NOSETUP  // ablation (wrong results): set-up only once per patch
     if (!(phase & 0x80000000u)) {
-      dp_setup_views(views, n_views, vis + k0, kc, s, f, recs, lane, kTma);
+      dp_setup_views<32>(views, n_views, vis + k0, kc, kc, s, f, recs, lane, kTma);
       phase |= 0x80000000u;
     }
 #else
-    dp_setup_views(views, n_views, vis + k0, kc, s, f, recs, lane, kTma);
+    dp_setup_views<32>(views, n_views, vis + k0, kc, kc, s, f, recs, lane, kTma);
 #endif
     __syncwarp();
     if (kTma && lane == 0 && recs[0].ok && recs[0].tmap != nullptr)  // first box of the round

@@ -60,7 +60,8 @@ extern "C" int dp_build_pyramid(dp_context *ctx, int n_levels) {
       d.width = (s.width + 1) / 2;
       d.height = (s.height + 1) / 2;
       d.pitch_px = (d.width + 31) & ~31;
-      DP_CUDA(ctx, cudaMalloc(&d.img, (size_t)d.pitch_px * d.height * sizeof(uint32_t)));
+      DP_CUDA(ctx, cudaMalloc(&d.img, (size_t)d.pitch_px * (d.height + 1) * sizeof(uint32_t)));  // + spare row
+      DP_CUDA(ctx, cudaMemsetAsync(d.img + (size_t)d.pitch_px * d.height, 0, (size_t)d.pitch_px * 4, st));
       dim3 grid((d.pitch_px + 255) / 256, d.height);
       dp_pyrdown_kernel<<<grid, 256, 0, st>>>(s.img, s.width, s.height, s.pitch_px, d.img, d.width,
                                               d.height, d.pitch_px);
