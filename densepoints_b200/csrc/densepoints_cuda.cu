@@ -446,13 +446,13 @@ template <int NP>
 static cudaError_t launch_refine_group(const DpRefineArgs &a, int sm_count, cudaStream_t st) {
   int per_sm = 1;
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dp_refine_group_kernel<NP>,
-                                                                DP_RWARPS * 32, 0);
+                                                                DP_GWARPS * 32, 0);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
-  const long long per_cta = (long long)DP_RWARPS * DP_GROUPS;
+  const long long per_cta = (long long)DP_GWARPS * DP_GROUPS;
   long long want = ((long long)a.p.n + per_cta - 1) / per_cta;
   long long grid = std::min<long long>(want, (long long)sm_count * per_sm);
-  dp_refine_group_kernel<NP><<<(unsigned)grid, DP_RWARPS * 32, 0, st>>>(a);
+  dp_refine_group_kernel<NP><<<(unsigned)grid, DP_GWARPS * 32, 0, st>>>(a);
   return cudaGetLastError();
 }
 

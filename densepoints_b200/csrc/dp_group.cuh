@@ -25,6 +25,15 @@
 #define DP_GL 4                  // lanes per patch (measured: 4 > 8 > 16 on B200 at s = 7)
 #endif
 #define DP_GROUPS (32 / DP_GL)   // patches per warp
+#ifndef DP_GWARPS
+#define DP_GWARPS 4              // warps per CTA of the group kernel
+#endif
+#ifndef DP_GMINCTA
+#define DP_GMINCTA 4             // resident CTAs per SM asked for (register cap 128)
+#endif
+#ifndef DP_GROUP_ROLLED
+#define DP_GROUP_ROLLED 1        // texel pass as a software-pipelined loop (else fully unrolled)
+#endif
 #define DP_GROUND DP_GL          // views per round of a group: one per lane in phase C
 
 struct DpGroupLane {
@@ -233,6 +242,92 @@ __device__ __forceinline__ void dp_unparametrize_g(const double C[3], const doub
   n[2] = xadd(xadd(xmul(xmul(ca, sb), n0[0]), xmul(-sa, n0[1])), xmul(xmul(ca, cb), n0[2]));
 }
 
+// ---- rolled, software-pipelined texel pass ---------------------------------------------
+// The fully unrolled pass of dp_view_texture is NP x ~85 instructions per view (18 KB of
+// straight-line code at NP = 13): ncu showed 14 % of the warp samples stalled on instruction
+// fetch and 23 % on the tap loads.  Here the pass is a loop: the taps of texel j+1 are
+// requested before texel j is blended (their latency hides behind ~45 instructions of
+// arithmetic), the gray values go to a byte per (pass, lane) in shared memory (they are
+// needed again once the mean is known) and the integer moments accumulate on the fly.
+struct DpTaps {
+  uint32_t p00, p01, p10, p11;
+  unsigned wx1, wy1;
+};
+
+struct DpWarpConsts {  // one view, from its set-up record
+  double M0, M1, M2, M3, M4, M5, M6, M7;
+  const uint32_t *src;
+  int pitch, xmax, ymax;
+};
+
+__device__ __forceinline__ void dp_texel_fetch(const DpWarpConsts &c, const double2 xy, DpTaps &t) {
+  const double x = xy.x, y = xy.y;
+  const double Wd = fma(c.M6, x, fma(c.M7, y, 1.0));
+  double r = dp_rcp(Wd);
+  r = (Wd != 0.0) ? r : 0.0;  // W ? INTER_TAB_SIZE / W : 0
+  const double fX = fma(c.M0, x, fma(c.M1, y, c.M2)) * r;
+  const double fY = fma(c.M3, x, fma(c.M4, y, c.M5)) * r;
+  const int Xi = __double2int_rn(fX);  // saturate_cast<int>(cvRound), half to even
+  const int Yi = __double2int_rn(fY);
+  // BORDER_REPLICATE as a clamp of the 1/32-px coordinate (see dp_view_texture)
+  const int Xc = min(max(Xi, 0), c.xmax), Yc = min(max(Yi, 0), c.ymax);
+  const int x0 = Xc >> 5, y0 = Yc >> 5;  // INTER_BITS = 5
+  t.wx1 = (unsigned)(Xc & 31);
+  t.wy1 = (unsigned)(Yc & 31);
+  const uint32_t *r0 = c.src + (unsigned)(y0 * c.pitch + x0), *r1 = r0 + c.pitch;
+  t.p00 = __ldg(r0); t.p01 = __ldg(r0 + 1);
+  t.p10 = __ldg(r1); t.p11 = __ldg(r1 + 1);
+}
+
+__device__ __forceinline__ int dp_texel_blend(const DpTaps &t) {
+  const uint32_t wx1 = t.wx1, wx0 = 32u - wx1, wy1 = t.wy1, wy0 = 32u - wy1;
+  const uint32_t br0 = (t.p00 & 0x00ff00ffu) * wx0 + (t.p01 & 0x00ff00ffu) * wx1;  // B | R<<16
+  const uint32_t br1 = (t.p10 & 0x00ff00ffu) * wx0 + (t.p11 & 0x00ff00ffu) * wx1;
+  const uint32_t g0 = (t.p00 & 0xff00u) * wx0 + (t.p01 & 0xff00u) * wx1;  // G << 8
+  const uint32_t g1 = (t.p10 & 0xff00u) * wx0 + (t.p11 & 0xff00u) * wx1;
+  const uint32_t B = ((br0 & 0xffffu) * wy0 + (br1 & 0xffffu) * wy1 + 512u) >> 10;
+  const uint32_t Rr = ((br0 >> 16) * wy0 + (br1 >> 16) * wy1 + 512u) >> 10;
+  const uint32_t G = (g0 * wy0 + g1 * wy1 + (512u << 8)) >> 18;
+  // cv::cvtColor(BGR2GRAY), 8U: 15-bit fixed point
+  return (int)((3735u * B + 19235u * G + 9798u * Rr + (1u << 14)) >> 15);
+}
+
+#ifndef DP_TEXEL_UNROLL
+#define DP_TEXEL_UNROLL 4  // measured: 1: 2.34, 2: 2.42, 4: 2.64, 7: 2.58, 13: 2.34 G evals/s
+#endif
+// (Measured and rejected: prefetch.global.L1 of the next view's ROI rows while the current
+// view is computed, -5 %.)
+
+// gs: this lane's column of the warp's gray buffer, gs[32 * j] = texel j (0 past the patch).
+template <int NP>
+__device__ __forceinline__ void dp_view_texture_rolled(const DpViewSetup &R, int npx,
+                                                       const double2 *txy, int sub, uint8_t *gs,
+                                                       unsigned &ma, unsigned &mb) {
+  DpWarpConsts c;
+  c.M0 = R.M[0]; c.M1 = R.M[1]; c.M2 = R.M[2]; c.M3 = R.M[3];
+  c.M4 = R.M[4]; c.M5 = R.M[5]; c.M6 = R.M[6]; c.M7 = R.M[7];
+  c.src = R.src;
+  c.pitch = R.pitch;
+  c.xmax = (R.rw - 1) << 5;
+  c.ymax = (R.rh - 1) << 5;
+  ma = 0;
+  mb = 0;
+  DpTaps cur;
+  dp_texel_fetch(c, txy[0], cur);
+  constexpr int kUnroll = DP_TEXEL_UNROLL;
+#pragma unroll kUnroll
+  for (int j = 0; j < NP; ++j) {
+    DpTaps nxt = cur;
+    if (j + 1 < NP) dp_texel_fetch(c, txy[DP_GL * (j + 1)], nxt);
+    int gray = dp_texel_blend(cur);
+    gray = (sub + DP_GL * j < npx) ? gray : 0;
+    gs[32 * j] = (uint8_t)gray;
+    ma += (unsigned)gray;
+    mb += (unsigned)(gray * gray);
+    cur = nxt;
+  }
+}
+
 // PatchOptimizationOpenCVFunctor::calc for the four patches of the warp at once: mean of
 // (1 - NCC) over the visible views in view order (optimization_opencv.cpp:17-35).  nv = 0
 // marks a group that does not evaluate (no patch, < 2 views, bad reference image).
@@ -241,8 +336,8 @@ template <int NP>
 __device__ __forceinline__ double dp_objective_g(const DpViewDev *__restrict__ views, int n_views,
                                                  int ref, const int32_t *vis, int nv, int s, int npx,
                                                  const double n[3], const double p[3],
-                                                 DpViewSetup *recs, const DpTexelTable &tx, int lane,
-                                                 const DpGroupLane &L) {
+                                                 DpViewSetup *recs, const DpTexelTable &tx,
+                                                 uint8_t *gs, int lane, const DpGroupLane &L) {
   DpFrame f;
   dp_make_frame(views + ref, s, n, p, f);
   if (nv == 0) f.ok = false;
@@ -270,13 +365,19 @@ __device__ __forceinline__ double dp_objective_g(const DpViewDev *__restrict__ v
       double num = 0.0;
       if (ok) {
         int g[NP];
-        dp_view_texture<NP, false, false, DP_GL, DpTexelTable>(R, npx, tx, nullptr, L.sub, g, nullptr);
         unsigned ma = 0, mb = 0;
+#if DP_GROUP_ROLLED
+        dp_view_texture_rolled<NP>(R, npx, tx.t, L.sub, gs, ma, mb);
+#pragma unroll
+        for (int j = 0; j < NP; ++j) g[j] = gs[32 * j];  // own column: no barrier needed
+#else
+        dp_view_texture<NP, false, false, DP_GL, DpTexelTable>(R, npx, tx, nullptr, L.sub, g, nullptr);
 #pragma unroll
         for (int j = 0; j < NP; ++j) {
           ma += (unsigned)g[j];
           mb += (unsigned)(g[j] * g[j]);
         }
+#endif
         s1 = dp_group_sum(ma, L.mask);  // exact integer moments (cv::meanStdDev's sums)
         s2 = dp_group_sum(mb, L.mask);
         // fl32(g_i - fl32(mean)): `Mat - scalar` on CV_32F (error_measurements.cpp:54)
@@ -319,10 +420,11 @@ __device__ __forceinline__ double dp_objective_g(const DpViewDev *__restrict__ v
 }
 
 template <int NP>
-__global__ void __launch_bounds__(DP_RWARPS * 32, DP_RMINCTA) dp_refine_group_kernel(DpRefineArgs a) {
-  __shared__ DpViewSetup recs_s[DP_RWARPS][DP_GROUPS][DP_GROUND];
-  __shared__ DpNelderMead nm_s[DP_RWARPS][DP_GROUPS];
+__global__ void __launch_bounds__(DP_GWARPS * 32, DP_GMINCTA) dp_refine_group_kernel(DpRefineArgs a) {
+  __shared__ DpViewSetup recs_s[DP_GWARPS][DP_GROUPS][DP_GROUND];
+  __shared__ DpNelderMead nm_s[DP_GWARPS][DP_GROUPS];
   __shared__ double2 txy_s[NP * DP_GL];
+  __shared__ uint8_t gray_s[DP_GWARPS][DP_GROUP_ROLLED ? NP : 1][32];
   const int s = a.p.s, npx = s * s;
   for (int t = threadIdx.x; t < NP * DP_GL; t += blockDim.x) {
     const int tt = t < npx ? t : 0;  // lanes past the last texel work on texel 0, masked later
@@ -409,7 +511,7 @@ __global__ void __launch_bounds__(DP_RWARPS * 32, DP_RMINCTA) dp_refine_group_ke
     }
     const int nv_eval = (have && nv >= 2 && ref_ok) ? nv : 0;
     const double fobj = dp_objective_g<NP>(a.p.views, a.p.n_views, ref_ok ? ref : 0, vis, nv_eval, s,
-                                           npx, n, p, recs, tx, lane, L);
+                                           npx, n, p, recs, tx, &gray_s[warp][0][lane], lane, L);
     const double fval = nv_eval ? fobj : 2.0;  // scores.size() == 0 (optimization_opencv.cpp:30-32)
     // ---- 3. Nelder-Mead bookkeeping of each group (diverges by solver state, short) ---------
     if (have) {
