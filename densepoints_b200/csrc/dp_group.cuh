@@ -249,6 +249,24 @@ __device__ __forceinline__ void dp_unparametrize_g(const double C[3], const doub
 // requested before texel j is blended (their latency hides behind ~45 instructions of
 // arithmetic), the gray values go to a byte per (pass, lane) in shared memory (they are
 // needed again once the mean is known) and the integer moments accumulate on the fly.
+// Per-group staging tile: DP_GTILE_H rows of DP_GTILE_W pixels, filled with 16-byte cp.async
+// copies (one per row and lane: 4 lanes x 4 pixels).  The window starts at the ROI origin
+// rounded down to 4 pixels (16-byte alignment), the taps carry the 0-3 pixel offset.
+#define DP_GTILE_W 16
+#define DP_GTILE_H 8
+#define DP_GTILE_STRIDE (DP_GTILE_W * DP_GTILE_H + 4)  // +4 words: stagger the groups over the banks
+#ifndef DP_GROUP_STAGE
+#define DP_GROUP_STAGE 1
+#endif
+
+__device__ __forceinline__ void dp_cp_async16(uint32_t *dst, const uint32_t *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dp_smem_u32(dst)), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void dp_cp_async_wait_all() {
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
 struct DpTaps {
   uint32_t p00, p01, p10, p11;
   unsigned wx1, wy1;
@@ -260,6 +278,7 @@ struct DpWarpConsts {  // one view, from its set-up record
   int pitch, xmax, ymax;
 };
 
+template <bool STAGED>
 __device__ __forceinline__ void dp_texel_fetch(const DpWarpConsts &c, const double2 xy, DpTaps &t) {
   const double x = xy.x, y = xy.y;
   const double Wd = fma(c.M6, x, fma(c.M7, y, 1.0));
@@ -274,9 +293,15 @@ __device__ __forceinline__ void dp_texel_fetch(const DpWarpConsts &c, const doub
   const int x0 = Xc >> 5, y0 = Yc >> 5;  // INTER_BITS = 5
   t.wx1 = (unsigned)(Xc & 31);
   t.wy1 = (unsigned)(Yc & 31);
-  const uint32_t *r0 = c.src + (unsigned)(y0 * c.pitch + x0), *r1 = r0 + c.pitch;
-  t.p00 = __ldg(r0); t.p01 = __ldg(r0 + 1);
-  t.p10 = __ldg(r1); t.p11 = __ldg(r1 + 1);
+  if (STAGED) {  // c.src = the group's tile (+ column offset), rows of DP_GTILE_W pixels
+    const uint32_t *r0 = c.src + (y0 * DP_GTILE_W + x0);
+    t.p00 = r0[0]; t.p01 = r0[1];
+    t.p10 = r0[DP_GTILE_W]; t.p11 = r0[DP_GTILE_W + 1];
+  } else {
+    const uint32_t *r0 = c.src + (unsigned)(y0 * c.pitch + x0), *r1 = r0 + c.pitch;
+    t.p00 = __ldg(r0); t.p01 = __ldg(r0 + 1);
+    t.p10 = __ldg(r1); t.p11 = __ldg(r1 + 1);
+  }
 }
 
 __device__ __forceinline__ int dp_texel_blend(const DpTaps &t) {
@@ -293,15 +318,39 @@ __device__ __forceinline__ int dp_texel_blend(const DpTaps &t) {
 }
 
 #ifndef DP_TEXEL_UNROLL
-#define DP_TEXEL_UNROLL 4  // measured: 1: 2.34, 2: 2.42, 4: 2.64, 7: 2.58, 13: 2.34 G evals/s
+#define DP_TEXEL_UNROLL 2  // measured with the staged tile: 1: 2.62, 2: 2.76, 3: 2.53, 4: 2.65, 6: 2.55 G evals/s
 #endif
 // (Measured and rejected: prefetch.global.L1 of the next view's ROI rows while the current
 // view is computed, -5 %.)
 
 // gs: this lane's column of the warp's gray buffer, gs[32 * j] = texel j (0 past the patch).
+template <int NP, bool STAGED>
+__device__ __forceinline__ void dp_texel_loop(const DpWarpConsts &c, int npx, const double2 *txy,
+                                              int sub, uint8_t *gs, unsigned &ma, unsigned &mb) {
+  DpTaps cur;
+  dp_texel_fetch<STAGED>(c, txy[0], cur);
+  constexpr int kUnroll = DP_TEXEL_UNROLL;
+#pragma unroll kUnroll
+  for (int j = 0; j < NP; ++j) {
+    DpTaps nxt = cur;
+    if (j + 1 < NP) dp_texel_fetch<STAGED>(c, txy[DP_GL * (j + 1)], nxt);
+    int gray = dp_texel_blend(cur);
+    gray = (sub + DP_GL * j < npx) ? gray : 0;
+    gs[32 * j] = (uint8_t)gray;
+    ma += (unsigned)gray;
+    mb += (unsigned)(gray * gray);
+    cur = nxt;
+  }
+}
+
+// tile: the group's staging tile (DP_GROUP_STAGE) -- every evaluation reads its ROIs from L2
+// again (128 patches x 5 views per SM do not stay in L1), and with 8 patches per warp nearly
+// every tap load had at least one lane missing L1; staged, the ROI is requested once, all rows
+// at the same time, and the 4 x NP taps per lane are shared-memory reads.
 template <int NP>
 __device__ __forceinline__ void dp_view_texture_rolled(const DpViewSetup &R, int npx,
-                                                       const double2 *txy, int sub, uint8_t *gs,
+                                                       const double2 *txy, uint32_t *tile,
+                                                       const DpGroupLane &L, uint8_t *gs,
                                                        unsigned &ma, unsigned &mb) {
   DpWarpConsts c;
   c.M0 = R.M[0]; c.M1 = R.M[1]; c.M2 = R.M[2]; c.M3 = R.M[3];
@@ -312,20 +361,28 @@ __device__ __forceinline__ void dp_view_texture_rolled(const DpViewSetup &R, int
   c.ymax = (R.rh - 1) << 5;
   ma = 0;
   mb = 0;
-  DpTaps cur;
-  dp_texel_fetch(c, txy[0], cur);
-  constexpr int kUnroll = DP_TEXEL_UNROLL;
-#pragma unroll kUnroll
-  for (int j = 0; j < NP; ++j) {
-    DpTaps nxt = cur;
-    if (j + 1 < NP) dp_texel_fetch(c, txy[DP_GL * (j + 1)], nxt);
-    int gray = dp_texel_blend(cur);
-    gray = (sub + DP_GL * j < npx) ? gray : 0;
-    gs[32 * j] = (uint8_t)gray;
-    ma += (unsigned)gray;
-    mb += (unsigned)(gray * gray);
-    cur = nxt;
+#if DP_GROUP_STAGE && DP_GL == 4
+  // image rows are 128-byte aligned, so the pixel offset of the ROI inside its 16-byte
+  // quad is visible in the pointer
+  const int xoff = (int)((reinterpret_cast<uintptr_t>(R.src) >> 2) & 3u);
+  const int wv = (R.rw + xoff + 3) >> 2;  // 16-byte pieces per row
+  if (wv <= DP_GTILE_W / 4 && R.rh <= DP_GTILE_H) {  // uniform inside the group
+    __syncwarp(L.mask);  // the previous view's taps are done with the tile
+    if (L.sub < wv) {
+      const uint32_t *g = R.src - xoff + 4 * L.sub;
+      uint32_t *d = tile + 4 * L.sub;
+#pragma unroll
+      for (int r = 0; r < DP_GTILE_H; ++r)
+        if (r < R.rh) dp_cp_async16(d + r * DP_GTILE_W, g + (size_t)r * R.pitch);
+    }
+    dp_cp_async_wait_all();
+    __syncwarp(L.mask);
+    c.src = tile + xoff;
+    dp_texel_loop<NP, true>(c, npx, txy, L.sub, gs, ma, mb);
+    return;
   }
+#endif
+  dp_texel_loop<NP, false>(c, npx, txy, L.sub, gs, ma, mb);
 }
 
 // PatchOptimizationOpenCVFunctor::calc for the four patches of the warp at once: mean of
@@ -337,7 +394,8 @@ __device__ __forceinline__ double dp_objective_g(const DpViewDev *__restrict__ v
                                                  int ref, const int32_t *vis, int nv, int s, int npx,
                                                  const double n[3], const double p[3],
                                                  DpViewSetup *recs, const DpTexelTable &tx,
-                                                 uint8_t *gs, int lane, const DpGroupLane &L) {
+                                                 uint8_t *gs, uint32_t *tile, int lane,
+                                                 const DpGroupLane &L) {
   DpFrame f;
   dp_make_frame(views + ref, s, n, p, f);
   if (nv == 0) f.ok = false;
@@ -367,7 +425,7 @@ __device__ __forceinline__ double dp_objective_g(const DpViewDev *__restrict__ v
         int g[NP];
         unsigned ma = 0, mb = 0;
 #if DP_GROUP_ROLLED
-        dp_view_texture_rolled<NP>(R, npx, tx.t, L.sub, gs, ma, mb);
+        dp_view_texture_rolled<NP>(R, npx, tx.t, tile, L, gs, ma, mb);
 #pragma unroll
         for (int j = 0; j < NP; ++j) g[j] = gs[32 * j];  // own column: no barrier needed
 #else
@@ -425,6 +483,8 @@ __global__ void __launch_bounds__(DP_GWARPS * 32, DP_GMINCTA) dp_refine_group_ke
   __shared__ DpNelderMead nm_s[DP_GWARPS][DP_GROUPS];
   __shared__ double2 txy_s[NP * DP_GL];
   __shared__ uint8_t gray_s[DP_GWARPS][DP_GROUP_ROLLED ? NP : 1][32];
+  // +32 words: the neighbour taps of an edge pixel (weight 0) may read past the last tile
+  __shared__ __align__(16) uint32_t tile_s[DP_GROUP_STAGE ? DP_GWARPS * DP_GROUPS * DP_GTILE_STRIDE + 32 : 4];
   const int s = a.p.s, npx = s * s;
   for (int t = threadIdx.x; t < NP * DP_GL; t += blockDim.x) {
     const int tt = t < npx ? t : 0;  // lanes past the last texel work on texel 0, masked later
@@ -511,7 +571,9 @@ __global__ void __launch_bounds__(DP_GWARPS * 32, DP_GMINCTA) dp_refine_group_ke
     }
     const int nv_eval = (have && nv >= 2 && ref_ok) ? nv : 0;
     const double fobj = dp_objective_g<NP>(a.p.views, a.p.n_views, ref_ok ? ref : 0, vis, nv_eval, s,
-                                           npx, n, p, recs, tx, &gray_s[warp][0][lane], lane, L);
+                                           npx, n, p, recs, tx, &gray_s[warp][0][lane],
+                                           tile_s + (DP_GROUP_STAGE ? (warp * DP_GROUPS + grp) * DP_GTILE_STRIDE : 0),
+                                           lane, L);
     const double fval = nv_eval ? fobj : 2.0;  // scores.size() == 0 (optimization_opencv.cpp:30-32)
     // ---- 3. Nelder-Mead bookkeeping of each group (diverges by solver state, short) ---------
     if (have) {
