@@ -361,10 +361,56 @@ static DpPatchArgs patch_args(dp_context *ctx, const dp_patch_dev *p, int s) {
   return a;
 }
 
+// Work order for the kernels that process several patches per warp in lockstep, and for the
+// persistent refine warps: patches by descending view count (counting sort, 3 tiny kernels).
+// Results do not depend on the order.  Small batches keep their natural order (*order = null).
+static int build_order(dp_context *ctx, const int32_t *nvis, const uint8_t *mask, int n,
+                       cudaStream_t st, const int32_t **order_out) {
+  *order_out = nullptr;
+  if (n < 4096) return DP_OK;
+  DP_CUDA(ctx, ctx->s_order.ensure((size_t)n * 4 + DP_ORDER_BINS * 4));
+  int32_t *order = ctx->s_order.as<int32_t>();
+  unsigned int *hist = reinterpret_cast<unsigned int *>(order + n);
+  DP_CUDA(ctx, cudaMemsetAsync(hist, 0, DP_ORDER_BINS * 4, st));
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  dp_order_hist_kernel<<<blocks, 256, 0, st>>>(nvis, mask, n, hist);
+  dp_order_scan_kernel<<<1, 1, 0, st>>>(hist);
+  dp_order_scatter_kernel<<<blocks, 256, 0, st>>>(nvis, mask, n, hist, order);
+  ctx->launches += 3;
+  *order_out = order;
+  return DP_OK;
+}
+
+#ifndef DP_SCORE_GROUP
+#define DP_SCORE_GROUP 1  // cells up to 8x8: several patches per warp (dp_group.cuh)
+#endif
+
 template <bool TEX, bool FILT>
-static void launch_score(const DpScoreArgs &a, int npass, cudaStream_t st) {
+static int launch_score(dp_context *ctx, const DpScoreArgs &a, int cell_size, cudaStream_t st) {
+  if (DP_SCORE_GROUP && cell_size <= 8) {
+    const int32_t *order = nullptr;
+    int rc = build_order(ctx, a.p.nvis, nullptr, a.p.n, st, &order);
+    if (rc != DP_OK) return rc;
+    const long long per_cta = (long long)DP_GWARPS * DP_GROUPS;
+    const unsigned grid = (unsigned)((a.p.n + per_cta - 1) / per_cta);
+#define DP_GCASE(S)                                                                             \
+  case S:                                                                                       \
+    dp_score_group_kernel<(S * S + DP_GL - 1) / DP_GL, TEX, FILT><<<grid, DP_GWARPS * 32, 0, st>>>( \
+        a, order);                                                                              \
+    break
+    switch (cell_size) {  // texel passes of a group = ceil(s^2 / DP_GL)
+      DP_GCASE(2); DP_GCASE(3); DP_GCASE(4); DP_GCASE(5); DP_GCASE(6); DP_GCASE(7);
+      default:
+        dp_score_group_kernel<(64 + DP_GL - 1) / DP_GL, TEX, FILT><<<grid, DP_GWARPS * 32, 0, st>>>(
+            a, order);
+        break;
+    }
+#undef DP_GCASE
+    ++ctx->launches;
+    return DP_OK;
+  }
   const unsigned grid = (unsigned)((a.p.n + DP_WARPS - 1) / DP_WARPS);
-  switch (npass) {
+  switch (npass_for(cell_size)) {
     case 1: dp_score_kernel<1, TEX, FILT><<<grid, DP_WARPS * 32, 0, st>>>(a); break;
     case 2: dp_score_kernel<2, TEX, FILT><<<grid, DP_WARPS * 32, 0, st>>>(a); break;
     case 4: dp_score_kernel<4, TEX, FILT><<<grid, DP_WARPS * 32, 0, st>>>(a); break;
@@ -372,6 +418,8 @@ static void launch_score(const DpScoreArgs &a, int npass, cudaStream_t st) {
     case 16: dp_score_kernel<16, TEX, FILT><<<grid, DP_WARPS * 32, 0, st>>>(a); break;
     default: dp_score_kernel<32, TEX, FILT><<<grid, DP_WARPS * 32, 0, st>>>(a); break;
   }
+  ++ctx->launches;
+  return DP_OK;
 }
 
 extern "C" int dp_score_dev(dp_context *ctx, const dp_patch_dev *p, int cell_size, float *ncc,
@@ -390,16 +438,15 @@ extern "C" int dp_score_dev(dp_context *ctx, const dp_patch_dev *p, int cell_siz
   a.thr = 0;
   a.min_visible = 0;
   a.keep = nullptr;
-  const int np = npass_for(cell_size);
   if (ncc) DP_CUDA(ctx, cudaMemsetAsync(ncc, 0, sizeof(float) * (size_t)p->n * p->vstride, st));
   if (valid) DP_CUDA(ctx, cudaMemsetAsync(valid, 0, (size_t)p->n * p->vstride, st));
   if (tex) {
     DP_CUDA(ctx, cudaMemsetAsync(tex, 0, (size_t)p->n * p->vstride * cell_size * cell_size * 3, st));
-    launch_score<true, false>(a, np, st);
+    rc = launch_score<true, false>(ctx, a, cell_size, st);
   } else {
-    launch_score<false, false>(a, np, st);
+    rc = launch_score<false, false>(ctx, a, cell_size, st);
   }
-  ++ctx->launches;
+  if (rc != DP_OK) return rc;
   DP_CUDA(ctx, cudaGetLastError());
   return DP_OK;
 }
@@ -420,8 +467,7 @@ extern "C" int dp_filter_dev(dp_context *ctx, dp_patch_dev *p, int cell_size, ui
   a.thr = ctx->prm.score_threshold;
   a.min_visible = ctx->prm.minimum_visible_image;
   a.keep = keep;
-  launch_score<false, true>(a, npass_for(cell_size), (cudaStream_t)stream);
-  ++ctx->launches;
+  if ((rc = launch_score<false, true>(ctx, a, cell_size, (cudaStream_t)stream)) != DP_OK) return rc;
   DP_CUDA(ctx, cudaGetLastError());
   return DP_OK;
 }
@@ -475,19 +521,7 @@ extern "C" int dp_refine_dev(dp_context *ctx, dp_patch_dev *p, int cell_size, co
   a.eps = ctx->prm.nm_eps;
   a.work_counter = ctx->work_counter.as<unsigned int>();
   a.mask = mask;
-  a.order = nullptr;
-  if (p->n >= 4096) {  // longest-first schedule (pays off once there are many waves of patches)
-    DP_CUDA(ctx, ctx->s_order.ensure((size_t)p->n * 4 + DP_ORDER_BINS * 4));
-    int32_t *order = ctx->s_order.as<int32_t>();
-    unsigned int *hist = reinterpret_cast<unsigned int *>(order + p->n);
-    DP_CUDA(ctx, cudaMemsetAsync(hist, 0, DP_ORDER_BINS * 4, st));
-    const unsigned blocks = (unsigned)((p->n + 255) / 256);
-    dp_order_hist_kernel<<<blocks, 256, 0, st>>>(p->nvis, mask, p->n, hist);
-    dp_order_scan_kernel<<<1, 1, 0, st>>>(hist);
-    dp_order_scatter_kernel<<<blocks, 256, 0, st>>>(p->nvis, mask, p->n, hist, order);
-    ctx->launches += 3;
-    a.order = order;
-  }
+  if ((rc = build_order(ctx, p->nvis, mask, p->n, st, &a.order)) != DP_OK) return rc;
   cudaError_t e;
   if (DP_REFINE_GROUP && cell_size <= 8) {
 #define DP_GCASE(S) case S: e = launch_refine_group<(S * S + DP_GL - 1) / DP_GL>(a, ctx->sm_count, st); break

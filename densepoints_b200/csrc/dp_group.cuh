@@ -31,9 +31,7 @@
 #ifndef DP_GMINCTA
 #define DP_GMINCTA 4             // resident CTAs per SM asked for (register cap 128)
 #endif
-#ifndef DP_GROUP_ROLLED
-#define DP_GROUP_ROLLED 1        // texel pass as a software-pipelined loop (else fully unrolled)
-#endif
+
 #define DP_GROUND DP_GL          // views per round of a group: one per lane in phase C
 
 struct DpGroupLane {
@@ -43,16 +41,8 @@ struct DpGroupLane {
   bool leader;     // sub == 0
 };
 
-// texel coordinates (x, y) as doubles, from a per-CTA table in shared memory: texel
-// sub + DP_GL*j of the lane is one LDS.128 at a constant offset from the lane's base pointer
-struct DpTexelTable {
-  const double2 *t;  // table + sub
-  __device__ __forceinline__ void get(int j, int, double &xo, double &yo) const {
-    const double2 v = t[DP_GL * j];
-    xo = v.x;
-    yo = v.y;
-  }
-};
+// Texel coordinates (x, y) come as doubles from a per-CTA table in shared memory: texel
+// sub + DP_GL*j of a lane is one LDS.128 at a constant offset from the lane's base pointer.
 
 template <typename T>
 __device__ __forceinline__ T dp_group_sum(T v, unsigned mask) {
@@ -304,7 +294,8 @@ __device__ __forceinline__ void dp_texel_fetch(const DpWarpConsts &c, const doub
   }
 }
 
-__device__ __forceinline__ int dp_texel_blend(const DpTaps &t) {
+__device__ __forceinline__ int dp_texel_blend(const DpTaps &t, uint32_t &Bo, uint32_t &Go,
+                                              uint32_t &Ro) {
   const uint32_t wx1 = t.wx1, wx0 = 32u - wx1, wy1 = t.wy1, wy0 = 32u - wy1;
   const uint32_t br0 = (t.p00 & 0x00ff00ffu) * wx0 + (t.p01 & 0x00ff00ffu) * wx1;  // B | R<<16
   const uint32_t br1 = (t.p10 & 0x00ff00ffu) * wx0 + (t.p11 & 0x00ff00ffu) * wx1;
@@ -313,6 +304,9 @@ __device__ __forceinline__ int dp_texel_blend(const DpTaps &t) {
   const uint32_t B = ((br0 & 0xffffu) * wy0 + (br1 & 0xffffu) * wy1 + 512u) >> 10;
   const uint32_t Rr = ((br0 >> 16) * wy0 + (br1 >> 16) * wy1 + 512u) >> 10;
   const uint32_t G = (g0 * wy0 + g1 * wy1 + (512u << 8)) >> 18;
+  Bo = B;
+  Go = G;
+  Ro = Rr;
   // cv::cvtColor(BGR2GRAY), 8U: 15-bit fixed point
   return (int)((3735u * B + 19235u * G + 9798u * Rr + (1u << 14)) >> 15);
 }
@@ -324,9 +318,10 @@ __device__ __forceinline__ int dp_texel_blend(const DpTaps &t) {
 // view is computed, -5 %.)
 
 // gs: this lane's column of the warp's gray buffer, gs[32 * j] = texel j (0 past the patch).
-template <int NP, bool STAGED>
+template <int NP, bool STAGED, bool WRITE_TEX>
 __device__ __forceinline__ void dp_texel_loop(const DpWarpConsts &c, int npx, const double2 *txy,
-                                              int sub, uint8_t *gs, unsigned &ma, unsigned &mb) {
+                                              int sub, uint8_t *gs, unsigned &ma, unsigned &mb,
+                                              uint8_t *__restrict__ tex_out) {
   DpTaps cur;
   dp_texel_fetch<STAGED>(c, txy[0], cur);
   constexpr int kUnroll = DP_TEXEL_UNROLL;
@@ -334,8 +329,15 @@ __device__ __forceinline__ void dp_texel_loop(const DpWarpConsts &c, int npx, co
   for (int j = 0; j < NP; ++j) {
     DpTaps nxt = cur;
     if (j + 1 < NP) dp_texel_fetch<STAGED>(c, txy[DP_GL * (j + 1)], nxt);
-    int gray = dp_texel_blend(cur);
-    gray = (sub + DP_GL * j < npx) ? gray : 0;
+    uint32_t B, G, Rr;
+    int gray = dp_texel_blend(cur, B, G, Rr);
+    const int i = sub + DP_GL * j;
+    gray = (i < npx) ? gray : 0;
+    if (WRITE_TEX && i < npx) {
+      tex_out[3 * i + 0] = (uint8_t)B;
+      tex_out[3 * i + 1] = (uint8_t)G;
+      tex_out[3 * i + 2] = (uint8_t)Rr;
+    }
     gs[32 * j] = (uint8_t)gray;
     ma += (unsigned)gray;
     mb += (unsigned)(gray * gray);
@@ -347,11 +349,12 @@ __device__ __forceinline__ void dp_texel_loop(const DpWarpConsts &c, int npx, co
 // again (128 patches x 5 views per SM do not stay in L1), and with 8 patches per warp nearly
 // every tap load had at least one lane missing L1; staged, the ROI is requested once, all rows
 // at the same time, and the 4 x NP taps per lane are shared-memory reads.
-template <int NP>
+template <int NP, bool WRITE_TEX>
 __device__ __forceinline__ void dp_view_texture_rolled(const DpViewSetup &R, int npx,
                                                        const double2 *txy, uint32_t *tile,
                                                        const DpGroupLane &L, uint8_t *gs,
-                                                       unsigned &ma, unsigned &mb) {
+                                                       unsigned &ma, unsigned &mb,
+                                                       uint8_t *__restrict__ tex_out) {
   DpWarpConsts c;
   c.M0 = R.M[0]; c.M1 = R.M[1]; c.M2 = R.M[2]; c.M3 = R.M[3];
   c.M4 = R.M[4]; c.M5 = R.M[5]; c.M6 = R.M[6]; c.M7 = R.M[7];
@@ -378,32 +381,35 @@ __device__ __forceinline__ void dp_view_texture_rolled(const DpViewSetup &R, int
     dp_cp_async_wait_all();
     __syncwarp(L.mask);
     c.src = tile + xoff;
-    dp_texel_loop<NP, true>(c, npx, txy, L.sub, gs, ma, mb);
+    dp_texel_loop<NP, true, WRITE_TEX>(c, npx, txy, L.sub, gs, ma, mb, tex_out);
     return;
   }
 #endif
-  dp_texel_loop<NP, false>(c, npx, txy, L.sub, gs, ma, mb);
+  dp_texel_loop<NP, false, WRITE_TEX>(c, npx, txy, L.sub, gs, ma, mb, tex_out);
 }
 
-// PatchOptimizationOpenCVFunctor::calc for the four patches of the warp at once: mean of
-// (1 - NCC) over the visible views in view order (optimization_opencv.cpp:17-35).  nv = 0
-// marks a group that does not evaluate (no patch, < 2 views, bad reference image).
-// Must be called by the whole warp.
-template <int NP>
-__device__ __forceinline__ double dp_objective_g(const DpViewDev *__restrict__ views, int n_views,
-                                                 int ref, const int32_t *vis, int nv, int s, int npx,
-                                                 const double n[3], const double p[3],
-                                                 DpViewSetup *recs, const DpTexelTable &tx,
-                                                 uint8_t *gs, uint32_t *tile, int lane,
-                                                 const DpGroupLane &L) {
+// Evaluate the visible views of the warp's patches in lockstep, DP_GROUND views per round:
+//   phase A  set-up of the round's views (one view of each patch per pass)
+//   phase B  per view: stage the ROI, warp the texels, integer moments, NCC numerator
+//   phase C  one view per lane of the group: NCCScore(texture 0, texture k)
+// After each round sink(k0, kc, kcmax, score) runs in warp-uniform code: lane `sub` of a group
+// holds the score of the group's view k0 + sub (sub < kc; -1 when either texture is empty,
+// error_measurements.cpp:38-40; the entry of view 0 is meaningless); kcmax is the largest kc in
+// the warp.  nv = 0 marks a group that does not evaluate.  Must be called by the whole warp.
+template <int NP, bool WRITE_TEX, typename Sink>
+__device__ __forceinline__ void dp_eval_views_g(const DpViewDev *__restrict__ views, int n_views,
+                                                int ref, bool ref_ok, const int32_t *vis, int nv,
+                                                int s, int npx, const double n[3], const double p[3],
+                                                DpViewSetup *recs, const double2 *txy, uint8_t *gs,
+                                                uint32_t *tile, int lane, const DpGroupLane &L,
+                                                uint8_t *tex_base, uint8_t *valid_base, Sink sink) {
   DpFrame f;
-  dp_make_frame(views + ref, s, n, p, f);
-  if (nv == 0) f.ok = false;
+  dp_make_frame(views + (ref_ok ? ref : 0), s, n, p, f);
+  if (!ref_ok) f.ok = false;  // every texture empty (optimization.cpp:45)
   const double scale = 1.0 / (double)npx;  // cv::meanStdDev: mean = sum * (1/N)
   float da[NP];                             // centred anchor texels (texture 0)
   unsigned a1 = 0, a2 = 0;
   bool a_ok = false;
-  double sum = 0.0;
   const int nvmax = __reduce_max_sync(DP_FULL, nv);
 #pragma unroll 1
   for (int k0 = 0; k0 < nvmax; k0 += DP_GROUND) {
@@ -422,23 +428,14 @@ __device__ __forceinline__ double dp_objective_g(const DpViewDev *__restrict__ v
       unsigned s1 = 0, s2 = 0;
       double num = 0.0;
       if (ok) {
-        int g[NP];
         unsigned ma = 0, mb = 0;
-#if DP_GROUP_ROLLED
-        dp_view_texture_rolled<NP>(R, npx, tx.t, tile, L, gs, ma, mb);
-#pragma unroll
-        for (int j = 0; j < NP; ++j) g[j] = gs[32 * j];  // own column: no barrier needed
-#else
-        dp_view_texture<NP, false, false, DP_GL, DpTexelTable>(R, npx, tx, nullptr, L.sub, g, nullptr);
-#pragma unroll
-        for (int j = 0; j < NP; ++j) {
-          ma += (unsigned)g[j];
-          mb += (unsigned)(g[j] * g[j]);
-        }
-#endif
+        dp_view_texture_rolled<NP, WRITE_TEX>(
+            R, npx, txy, tile, L, gs, ma, mb,
+            WRITE_TEX ? tex_base + (size_t)(k0 + l) * npx * 3 : nullptr);
         s1 = dp_group_sum(ma, L.mask);  // exact integer moments (cv::meanStdDev's sums)
         s2 = dp_group_sum(mb, L.mask);
-        // fl32(g_i - fl32(mean)): `Mat - scalar` on CV_32F (error_measurements.cpp:54)
+        // fl32(g_i - fl32(mean)): `Mat - scalar` on CV_32F (error_measurements.cpp:54); the
+        // lane reads back its own column of the gray buffer: no barrier needed
         const float mf = (float)xmul((double)s1, scale);
         if (k0 + l == 0) {
           a1 = s1;
@@ -446,11 +443,11 @@ __device__ __forceinline__ double dp_objective_g(const DpViewDev *__restrict__ v
           a_ok = true;
 #pragma unroll
           for (int j = 0; j < NP; ++j)
-            da[j] = (L.sub + DP_GL * j < npx) ? __fsub_rn((float)g[j], mf) : 0.f;
+            da[j] = (L.sub + DP_GL * j < npx) ? __fsub_rn((float)gs[32 * j], mf) : 0.f;
         } else if (a_ok) {
 #pragma unroll
           for (int j = 0; j < NP; ++j) {
-            const float db = (L.sub + DP_GL * j < npx) ? __fsub_rn((float)g[j], mf) : 0.f;
+            const float db = (L.sub + DP_GL * j < npx) ? __fsub_rn((float)gs[32 * j], mf) : 0.f;
             num = xadd(num, xmul((double)da[j], (double)db));
           }
           num = dp_group_sum(num, L.mask);
@@ -464,49 +461,145 @@ __device__ __forceinline__ double dp_objective_g(const DpViewDev *__restrict__ v
       }
     }
     // phase C, one view per lane of the group
-    double score = -1.0;  // empty texture (error_measurements.cpp:38-40)
+    double score = -1.0;
     if (L.sub < kc && k0 + L.sub >= 1 && myok && a_ok)
       score = dp_ncc_finish(a1, a2, my1, my2, mynum, scale, npx);
-    // std::accumulate of (1 - NCC) in view order (optimization_opencv.cpp:24, 34)
-    const double term = xsub(1.0, score);
-    for (int l = (k0 == 0 ? 1 : 0); l < kcmax; ++l) {
-      const double t = __shfl_sync(DP_FULL, term, L.base + l);
-      if (l < kc) sum = xadd(sum, t);
+    if (valid_base != nullptr && L.sub < kc) valid_base[k0 + L.sub] = (uint8_t)myok;
+    sink(k0, kc, kcmax, score);
+  }
+}
+
+// PatchOptimizationOpenCVFunctor::calc for all patches of the warp at once: mean of (1 - NCC)
+// over the visible views in view order (optimization_opencv.cpp:17-35).
+template <int NP>
+__device__ __forceinline__ double dp_objective_g(const DpViewDev *__restrict__ views, int n_views,
+                                                 int ref, const int32_t *vis, int nv, int s, int npx,
+                                                 const double n[3], const double p[3],
+                                                 DpViewSetup *recs, const double2 *txy,
+                                                 uint8_t *gs, uint32_t *tile, int lane,
+                                                 const DpGroupLane &L) {
+  double sum = 0.0;
+  dp_eval_views_g<NP, false>(
+      views, n_views, ref, true, vis, nv, s, npx, n, p, recs, txy, gs, tile, lane, L, nullptr, nullptr,
+      [&](int k0, int kc, int kcmax, double score) {
+        // std::accumulate of (1 - NCC) in view order (optimization_opencv.cpp:24, 34)
+        const double term = xsub(1.0, score);
+        for (int l = (k0 == 0 ? 1 : 0); l < kcmax; ++l) {
+          const double t = __shfl_sync(DP_FULL, term, L.base + l);
+          if (l < kc) sum = xadd(sum, t);
+        }
+      });
+  return nv >= 2 ? sum / (double)(nv - 1) : 2.0;  // scores.size() == 0 -> 2
+}
+
+// Shared memory of a CTA of the group kernels.
+template <int NP>
+struct DpGroupShared {
+  DpViewSetup recs[DP_GWARPS][DP_GROUPS][DP_GROUND];
+  double2 txy[NP * DP_GL];
+  // +32 words: the neighbour taps of an edge pixel (weight 0) may read past the last tile
+  __align__(16) uint32_t tile[DP_GROUP_STAGE ? DP_GWARPS * DP_GROUPS * DP_GTILE_STRIDE + 32 : 4];
+  uint8_t gray[DP_GWARPS][NP][32];
+  __device__ __forceinline__ void init_texels(int s, int npx) {
+    for (int t = threadIdx.x; t < NP * DP_GL; t += blockDim.x) {
+      const int tt = t < npx ? t : 0;  // lanes past the last texel work on texel 0, masked later
+      const int yy = tt / s;
+      txy[t] = make_double2((double)(tt - yy * s), (double)yy);
     }
   }
-  return nv >= 2 ? sum / (double)(nv - 1) : 2.0;  // scores.size() == 0 -> 2
+  __device__ __forceinline__ uint32_t *group_tile(int warp, int grp) {
+    return tile + (DP_GROUP_STAGE ? (warp * DP_GROUPS + grp) * DP_GTILE_STRIDE : 0);
+  }
+};
+
+__device__ __forceinline__ DpGroupLane dp_group_lane(int lane) {
+  DpGroupLane L;
+  L.sub = lane & (DP_GL - 1);
+  L.base = lane & ~(DP_GL - 1);
+  L.mask = (DP_GL == 32) ? DP_FULL : (((1u << DP_GL) - 1u) << L.base);
+  L.leader = L.sub == 0;
+  return L;
+}
+
+// K1+K2 for cells up to 8x8: GetProjectedTextures + NCCScore for every visible view and,
+// fused, FilterByErrorMeasurement's erase loop -- the warp-per-patch dp_score_kernel with
+// DP_GROUPS patches per warp.  Work item `slot` = patch order[slot] (patches sorted by view
+// count so that the patches of a warp run the same number of view steps), or patch `slot`.
+template <int NP, bool WRITE_TEX, bool FILTER>
+__global__ void __launch_bounds__(DP_GWARPS * 32, DP_GMINCTA)
+dp_score_group_kernel(DpScoreArgs a, const int32_t *__restrict__ order) {
+  __shared__ DpGroupShared<NP> sh;
+  const int s = a.p.s, npx = s * s;
+  sh.init_texels(s, npx);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const DpGroupLane L = dp_group_lane(lane);
+  const int grp = lane / DP_GL;
+  const long long slot = ((long long)blockIdx.x * DP_GWARPS + warp) * DP_GROUPS + grp;
+  const bool have = slot < a.p.n;
+  const long long i = have ? (order ? (long long)order[slot] : slot) : 0;
+  const int nv = have ? min(a.p.nvis[i], a.p.vstride) : 0;
+  const int ref = a.p.ref[i];
+  const bool ref_ok = ref >= 0 && ref < a.p.n_views;
+  double n[3] = {(double)a.p.nrm[3 * i], (double)a.p.nrm[3 * i + 1], (double)a.p.nrm[3 * i + 2]};
+  double p[3] = {(double)a.p.pos[3 * i], (double)a.p.pos[3 * i + 1], (double)a.p.pos[3 * i + 2]};
+  int32_t *vis = a.p.vis + (size_t)i * a.p.vstride;
+  float *ncc = a.ncc ? a.ncc + (size_t)i * a.p.vstride : nullptr;
+  uint8_t *tex = WRITE_TEX ? a.tex + (size_t)i * a.p.vstride * npx * 3 : nullptr;
+  uint8_t *valid = a.valid ? a.valid + (size_t)i * a.p.vstride : nullptr;
+  int wcur = 0;
+  const double thr = a.thr;
+  const unsigned lt = (1u << L.sub) - 1u;
+  dp_eval_views_g<NP, WRITE_TEX>(
+      a.p.views, a.p.n_views, ref, ref_ok, vis, nv, s, npx, n, p,
+      sh.recs[warp][grp], sh.txy + L.sub, &sh.gray[warp][0][lane], sh.group_tile(warp, grp), lane, L,
+      tex, valid, [&](int k0, int kc, int kcmax, double score) {
+        const int k = k0 + L.sub;
+        const bool mine = L.sub < kc && k >= 1;
+        if (ncc != nullptr && mine) ncc[k] = (float)score;
+        if (FILTER) {
+          // "drop original entry k-1 iff the score of entry k is low" (see dp_score_kernel),
+          // compacted in place with the group's bits of a warp ballot
+          const bool keepf = mine && !(score < thr);
+          const int prev = mine ? vis[k - 1] : -1;
+          const unsigned m = (__ballot_sync(DP_FULL, keepf) >> L.base) & ((1u << DP_GL) - 1u);
+          __syncwarp();
+          if (keepf) vis[wcur + __popc(m & lt)] = prev;
+          wcur += __popc(m);
+          __syncwarp();
+        }
+      });
+  if (FILTER && have) {
+    bool kept = false;
+    if (nv >= 2) {  // scores.size() > 0 (optimization.cpp:113)
+      if (L.leader) vis[wcur] = vis[nv - 1];
+      ++wcur;
+      __syncwarp(L.mask);
+      for (int k = wcur + L.sub; k < nv; k += DP_GL) vis[k] = -1;
+      if (L.leader) a.p.nvis[i] = wcur;
+      kept = wcur >= a.min_visible;  // optimization.cpp:127
+    }
+    if (L.leader) a.keep[i] = kept ? 1 : 0;
+  }
 }
 
 template <int NP>
 __global__ void __launch_bounds__(DP_GWARPS * 32, DP_GMINCTA) dp_refine_group_kernel(DpRefineArgs a) {
-  __shared__ DpViewSetup recs_s[DP_GWARPS][DP_GROUPS][DP_GROUND];
+  __shared__ DpGroupShared<NP> sh;
   __shared__ DpNelderMead nm_s[DP_GWARPS][DP_GROUPS];
-  __shared__ double2 txy_s[NP * DP_GL];
-  __shared__ uint8_t gray_s[DP_GWARPS][DP_GROUP_ROLLED ? NP : 1][32];
-  // +32 words: the neighbour taps of an edge pixel (weight 0) may read past the last tile
-  __shared__ __align__(16) uint32_t tile_s[DP_GROUP_STAGE ? DP_GWARPS * DP_GROUPS * DP_GTILE_STRIDE + 32 : 4];
   const int s = a.p.s, npx = s * s;
-  for (int t = threadIdx.x; t < NP * DP_GL; t += blockDim.x) {
-    const int tt = t < npx ? t : 0;  // lanes past the last texel work on texel 0, masked later
-    const int yy = tt / s;
-    txy_s[t] = make_double2((double)(tt - yy * s), (double)yy);
-  }
+  sh.init_texels(s, npx);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  DpGroupLane L;
-  L.sub = lane & (DP_GL - 1);
-  L.base = lane & ~(DP_GL - 1);
-  L.mask = ((1u << DP_GL) - 1u) << L.base;
-  L.leader = L.sub == 0;
+  const DpGroupLane L = dp_group_lane(lane);
   const int grp = lane / DP_GL;
-  DpViewSetup *recs = recs_s[warp][grp];
+  DpViewSetup *recs = sh.recs[warp][grp];
   DpNelderMead &S = nm_s[warp][grp];
   if (L.leader) {  // defined values for the lockstep evaluations of a group without a patch
     double *z = reinterpret_cast<double *>(&S);
     for (int j = 0; j < (int)(sizeof(DpNelderMead) / sizeof(double)); ++j) z[j] = 0.0;
   }
   __syncthreads();
-  DpTexelTable tx;
-  tx.t = txy_s + L.sub;
+  const double2 *txy = sh.txy + L.sub;
   bool have = false, exhausted = false;
   long long i = 0;
   int nv = 0, ref = 0;
@@ -571,9 +664,8 @@ __global__ void __launch_bounds__(DP_GWARPS * 32, DP_GMINCTA) dp_refine_group_ke
     }
     const int nv_eval = (have && nv >= 2 && ref_ok) ? nv : 0;
     const double fobj = dp_objective_g<NP>(a.p.views, a.p.n_views, ref_ok ? ref : 0, vis, nv_eval, s,
-                                           npx, n, p, recs, tx, &gray_s[warp][0][lane],
-                                           tile_s + (DP_GROUP_STAGE ? (warp * DP_GROUPS + grp) * DP_GTILE_STRIDE : 0),
-                                           lane, L);
+                                           npx, n, p, recs, txy, &sh.gray[warp][0][lane],
+                                           sh.group_tile(warp, grp), lane, L);
     const double fval = nv_eval ? fobj : 2.0;  // scores.size() == 0 (optimization_opencv.cpp:30-32)
     // ---- 3. Nelder-Mead bookkeeping of each group (diverges by solver state, short) ---------
     if (have) {
