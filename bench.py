@@ -13,7 +13,7 @@ Workload (N=1): BASELINE.json configs[1] -- synthetic textured sphere, 16 views
   value  = patch-view evals/s with the seeds resident in HBM (dp_*_dev entry points)
   e2e    = the same through the host-buffer C ABI (dp_filter + dp_refine on pinned host
            arrays, H2D/D2H inside the timed region)
-  roofline = the refine kernel against the measured HBM copy bandwidth
+  roofline = the refine kernel (dp_refine_group_kernel) against the measured HBM copy bandwidth
   cpu_baseline = the CPU oracle (OpenMP, all host threads) on a bounded sample
 
 `--impl reference` times the CPU oracle alone (the reference C++ cannot be built here:
@@ -333,13 +333,14 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak,
                 "traffic": cap["dram_bytes_per_launch"] if cap else None,
-                "kernel": "dp_refine_kernel<2>",
+                "kernel": cap["kernel"] if cap else "dp_refine_group_kernel<13>",
                 "kernel_ms": refine_kernel_ms, "peak_source": peak_src,
                 "alg_bytes_per_eval": b_alg(CELL, mean_nv), "alg_bytes_per_launch": alg_bytes,
                 "share_of_step": refine_kernel_ms * args.steps / gpu_ms,
-                "note": "the binding roof is instruction issue, not HBM: one patch-view eval is "
-                        "~530 warp instructions (ncu), the 79 MB BGRx image set is L2-resident "
-                        "and DRAM traffic is <1% of the algorithmic bytes"}
+                "note": "the binding roof is instruction issue and dependent-issue latency, not "
+                        "HBM: the 79 MB BGRx image set is L2-resident and DRAM traffic is <1% of "
+                        "the algorithmic bytes; see roofline.issue for warp instructions per "
+                        "patch-view eval and the issue-slot fraction (ncu)"}
     if cap:
         sm = 148
         issue_peak = sm * 4 * (clocks["sm_mhz"] or 1965.0) * 1e6       # warp-inst/s

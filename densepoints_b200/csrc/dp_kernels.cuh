@@ -272,12 +272,23 @@ struct DpRefineArgs {
 // handed out in descending view count (counting sort, 3 tiny kernels).  Results do not
 // depend on the order in which patches are processed.
 #define DP_ORDER_BINS 257
-__global__ void dp_order_hist_kernel(const int32_t *__restrict__ nvis, const uint8_t *__restrict__ mask,
-                                     int n, unsigned int *__restrict__ hist) {
+__device__ __forceinline__ int dp_order_key(const int32_t *__restrict__ nvis,
+                                            const uint8_t *__restrict__ mask, int i) {
+  return (mask && mask[i] == 0) ? 0 : min(max(nvis[i], 0), DP_ORDER_BINS - 1);
+}
+// A few bins receive almost all patches, so the global atomics are aggregated first: per CTA in
+// shared memory for the histogram, per group of equal keys in a warp for the scatter.
+__global__ void __launch_bounds__(256)
+dp_order_hist_kernel(const int32_t *__restrict__ nvis, const uint8_t *__restrict__ mask, int n,
+                     unsigned int *__restrict__ hist) {
+  __shared__ unsigned int h[DP_ORDER_BINS];
+  for (int b = threadIdx.x; b < DP_ORDER_BINS; b += blockDim.x) h[b] = 0;
+  __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int key = (mask && mask[i] == 0) ? 0 : min(max(nvis[i], 0), DP_ORDER_BINS - 1);
-  atomicAdd(hist + (DP_ORDER_BINS - 1 - key), 1u);  // bin 0 = most views
+  if (i < n) atomicAdd(h + (DP_ORDER_BINS - 1 - dp_order_key(nvis, mask, i)), 1u);  // bin 0 = most views
+  __syncthreads();
+  for (int b = threadIdx.x; b < DP_ORDER_BINS; b += blockDim.x)
+    if (h[b]) atomicAdd(hist + b, h[b]);
 }
 __global__ void dp_order_scan_kernel(unsigned int *hist) {  // exclusive scan in place, 1 thread
   unsigned int run = 0;
@@ -287,13 +298,19 @@ __global__ void dp_order_scan_kernel(unsigned int *hist) {  // exclusive scan in
     run += c;
   }
 }
-__global__ void dp_order_scatter_kernel(const int32_t *__restrict__ nvis, const uint8_t *__restrict__ mask,
-                                        int n, unsigned int *__restrict__ cursor,
-                                        int32_t *__restrict__ order) {
+__global__ void __launch_bounds__(256)
+dp_order_scatter_kernel(const int32_t *__restrict__ nvis, const uint8_t *__restrict__ mask, int n,
+                        unsigned int *__restrict__ cursor, int32_t *__restrict__ order) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int key = (mask && mask[i] == 0) ? 0 : min(max(nvis[i], 0), DP_ORDER_BINS - 1);
-  order[atomicAdd(cursor + (DP_ORDER_BINS - 1 - key), 1u)] = i;
+  const int lane = threadIdx.x & 31;
+  const bool in = i < n;
+  const int bin = in ? DP_ORDER_BINS - 1 - dp_order_key(nvis, mask, i) : -1;
+  const unsigned peers = __match_any_sync(DP_FULL, bin);  // lanes with my bin
+  const int leader = __ffs(peers) - 1;
+  unsigned int base = 0;
+  if (in && lane == leader) base = atomicAdd(cursor + bin, (unsigned)__popc(peers));
+  base = __shfl_sync(DP_FULL, base, leader);
+  if (in) order[base + __popc(peers & ((1u << lane) - 1u))] = i;
 }
 
 // Optimization::UnparametrizePatch (optimization.cpp:78-96)
