@@ -145,6 +145,9 @@ extern "C" void dp_destroy(dp_context *ctx) {
                       &ctx->org.claim, &ctx->org.pos, &ctx->org.nrm, &ctx->org.rgb, &ctx->org.ref,
                       &ctx->org.nvis, &ctx->org.vis};
   for (DpDevBuf *b : bufs) b->release();
+  for (cudaEvent_t e : ctx->pipe_events) cudaEventDestroy(e);
+  if (ctx->stream_in) cudaStreamDestroy(ctx->stream_in);
+  if (ctx->stream_out) cudaStreamDestroy(ctx->stream_out);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -335,6 +338,12 @@ int dp_sync_views(dp_context *ctx) {
 
 // ---------------------------------------------------------------------------------------
 // device-pointer layer
+
+static int check_patch_dev_args(dp_context *ctx, int cell_size) {
+  if (cell_size < 2 || cell_size > DP_MAX_CELL_SIZE)
+    return dp_fail(ctx, DP_ERR_INVALID_ARG, "cell_size must be in [2, 32]");
+  return DP_OK;
+}
 
 static int check_patch_dev(dp_context *ctx, const dp_patch_dev *p, int cell_size) {
   if (!ctx || !p) return DP_ERR_INVALID_ARG;
@@ -687,30 +696,106 @@ extern "C" int dp_refine(dp_context *ctx, dp_patch_soa *h, int cell_size, const 
   return DP_OK;
 }
 
+// Seed::OptimizeAndRefinePatches in one call, as a three-stream pipeline for pinned host
+// arrays: the batch is uploaded in chunks and each chunk is filtered as soon as it has landed
+// (the filter kernels are short and have no tail); the refinement then runs as ONE launch over
+// the whole batch -- its persistent warps end with a tail as long as the slowest patch, so
+// per-chunk refinement (measured: 8 chunks, -27 %) loses more than the overlap wins -- while
+// the filter's outputs (keep bits, visible sets: 2/3 of the download, read-only for the refine
+// kernel) are already on their way back; the refined geometry follows.
+#ifndef DP_PIPE_CHUNK
+#define DP_PIPE_CHUNK 131072
+#endif
 extern "C" int dp_filter_refine(dp_context *ctx, dp_patch_soa *h, int cell_size, uint8_t *keep,
                                 int32_t *evals) {
   if (!ctx) return DP_ERR_INVALID_ARG;
   if (!keep) return dp_fail(ctx, DP_ERR_INVALID_ARG, "keep is null");
-  dp_patch_dev d;
-  int rc = upload_patches(ctx, h, &d, true);
-  if (rc != DP_OK) return rc;
+  if (!h) return DP_ERR_INVALID_ARG;
+  if (h->n < 0 || h->vstride <= 0) return dp_fail(ctx, DP_ERR_INVALID_ARG, "patch batch shape");
   if (h->n == 0) return DP_OK;
+  if (!h->pos || !h->nrm || !h->ref || !h->nvis || !h->vis)
+    return dp_fail(ctx, DP_ERR_INVALID_ARG, "null patch array");
+  int rc = check_patch_dev_args(ctx, cell_size);
+  if (rc != DP_OK) return rc;
+  cudaSetDevice(ctx->device);
+  if ((rc = dp_sync_views(ctx)) != DP_OK) return rc;
   const size_t n = (size_t)h->n, vs = (size_t)h->vstride;
+  DP_CUDA(ctx, ctx->s_pos.ensure(n * 12));
+  DP_CUDA(ctx, ctx->s_nrm.ensure(n * 12));
+  DP_CUDA(ctx, ctx->s_ref.ensure(n * 4));
+  DP_CUDA(ctx, ctx->s_nvis.ensure(n * 4));
+  DP_CUDA(ctx, ctx->s_vis.ensure(n * vs * 4));
   DP_CUDA(ctx, ctx->s_keep.ensure(n));
-  if (evals) DP_CUDA(ctx, ctx->s_evals.ensure(n * 4));
-  cudaStream_t st = ctx->stream;
-  if ((rc = dp_filter_dev(ctx, &d, cell_size, ctx->s_keep.as<uint8_t>(), st)) != DP_OK) return rc;
-  if ((rc = dp_refine_dev(ctx, &d, cell_size, ctx->s_keep.as<uint8_t>(),
-                          evals ? ctx->s_evals.as<int32_t>() : nullptr, nullptr, st)) != DP_OK)
-    return rc;
-  DP_CUDA(ctx, cudaMemcpyAsync(keep, ctx->s_keep.ptr, n, cudaMemcpyDeviceToHost, st));
-  DP_CUDA(ctx, cudaMemcpyAsync(h->nvis, d.nvis, n * 4, cudaMemcpyDeviceToHost, st));
-  DP_CUDA(ctx, cudaMemcpyAsync(h->vis, d.vis, n * vs * 4, cudaMemcpyDeviceToHost, st));
-  DP_CUDA(ctx, cudaMemcpyAsync(h->pos, d.pos, n * 12, cudaMemcpyDeviceToHost, st));
-  DP_CUDA(ctx, cudaMemcpyAsync(h->nrm, d.nrm, n * 12, cudaMemcpyDeviceToHost, st));
-  if (evals) DP_CUDA(ctx, cudaMemcpyAsync(evals, ctx->s_evals.ptr, n * 4, cudaMemcpyDeviceToHost, st));
-  DP_CUDA(ctx, cudaStreamSynchronize(st));
-  return DP_OK;
+  DP_CUDA(ctx, ctx->s_evals.ensure(n * 4));
+  const size_t chunk = std::min<size_t>(n, DP_PIPE_CHUNK);
+  // scratch of the per-chunk launches, sized once so that no reallocation (= device-wide
+  // synchronisation) happens while the pipeline runs
+  DP_CUDA(ctx, ctx->s_order.ensure(n * 4 + DP_ORDER_BINS * 4));
+  DP_CUDA(ctx, ctx->work_counter.ensure(sizeof(unsigned int)));
+  if (!ctx->stream_in) {
+    DP_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream_in, cudaStreamNonBlocking));
+    DP_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream_out, cudaStreamNonBlocking));
+  }
+  const size_t n_chunks = (n + chunk - 1) / chunk;
+  while (ctx->pipe_events.size() < std::max<size_t>(2 * n_chunks, (size_t)4)) {
+    cudaEvent_t e;
+    DP_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->pipe_events.push_back(e);
+  }
+  cudaStream_t s_in = ctx->stream_in, s_cmp = ctx->stream, s_out = ctx->stream_out;
+  float *d_pos = ctx->s_pos.as<float>(), *d_nrm = ctx->s_nrm.as<float>();
+  int32_t *d_ref = ctx->s_ref.as<int32_t>(), *d_nvis = ctx->s_nvis.as<int32_t>(),
+          *d_vis = ctx->s_vis.as<int32_t>(), *d_evals = ctx->s_evals.as<int32_t>();
+  uint8_t *d_keep = ctx->s_keep.as<uint8_t>();
+  for (size_t c = 0; c < n_chunks; ++c) {
+    const size_t o = c * chunk, m = std::min(chunk, n - o);
+    DP_CUDA(ctx, cudaMemcpyAsync(d_pos + 3 * o, h->pos + 3 * o, m * 12, cudaMemcpyHostToDevice, s_in));
+    DP_CUDA(ctx, cudaMemcpyAsync(d_nrm + 3 * o, h->nrm + 3 * o, m * 12, cudaMemcpyHostToDevice, s_in));
+    DP_CUDA(ctx, cudaMemcpyAsync(d_ref + o, h->ref + o, m * 4, cudaMemcpyHostToDevice, s_in));
+    DP_CUDA(ctx, cudaMemcpyAsync(d_nvis + o, h->nvis + o, m * 4, cudaMemcpyHostToDevice, s_in));
+    DP_CUDA(ctx, cudaMemcpyAsync(d_vis + o * vs, h->vis + o * vs, m * vs * 4, cudaMemcpyHostToDevice, s_in));
+    DP_CUDA(ctx, cudaEventRecord(ctx->pipe_events[2 * c], s_in));
+  }
+  int first_rc = DP_OK;
+  dp_patch_dev d;
+  d.vstride = h->vstride;
+  d.rgb = nullptr;
+  for (size_t c = 0; c < n_chunks && first_rc == DP_OK; ++c) {
+    const size_t o = c * chunk, m = std::min(chunk, n - o);
+    d.n = (int32_t)m;
+    d.pos = d_pos + 3 * o;
+    d.nrm = d_nrm + 3 * o;
+    d.ref = d_ref + o;
+    d.nvis = d_nvis + o;
+    d.vis = d_vis + o * vs;
+    DP_CUDA(ctx, cudaStreamWaitEvent(s_cmp, ctx->pipe_events[2 * c], 0));
+    first_rc = dp_filter_dev(ctx, &d, cell_size, d_keep + o, s_cmp);
+  }
+  if (first_rc == DP_OK) {
+    DP_CUDA(ctx, cudaEventRecord(ctx->pipe_events[1], s_cmp));  // filter done
+    DP_CUDA(ctx, cudaStreamWaitEvent(s_out, ctx->pipe_events[1], 0));
+    DP_CUDA(ctx, cudaMemcpyAsync(keep, d_keep, n, cudaMemcpyDeviceToHost, s_out));
+    DP_CUDA(ctx, cudaMemcpyAsync(h->nvis, d_nvis, n * 4, cudaMemcpyDeviceToHost, s_out));
+    DP_CUDA(ctx, cudaMemcpyAsync(h->vis, d_vis, n * vs * 4, cudaMemcpyDeviceToHost, s_out));
+    d.n = h->n;
+    d.pos = d_pos;
+    d.nrm = d_nrm;
+    d.ref = d_ref;
+    d.nvis = d_nvis;
+    d.vis = d_vis;
+    first_rc = dp_refine_dev(ctx, &d, cell_size, d_keep, evals ? d_evals : nullptr, nullptr, s_cmp);
+  }
+  if (first_rc == DP_OK) {
+    DP_CUDA(ctx, cudaEventRecord(ctx->pipe_events[3], s_cmp));  // refine done
+    DP_CUDA(ctx, cudaStreamWaitEvent(s_out, ctx->pipe_events[3], 0));
+    DP_CUDA(ctx, cudaMemcpyAsync(h->pos, d_pos, n * 12, cudaMemcpyDeviceToHost, s_out));
+    DP_CUDA(ctx, cudaMemcpyAsync(h->nrm, d_nrm, n * 12, cudaMemcpyDeviceToHost, s_out));
+    if (evals) DP_CUDA(ctx, cudaMemcpyAsync(evals, d_evals, n * 4, cudaMemcpyDeviceToHost, s_out));
+  }
+  DP_CUDA(ctx, cudaStreamSynchronize(s_in));
+  DP_CUDA(ctx, cudaStreamSynchronize(s_cmp));
+  DP_CUDA(ctx, cudaStreamSynchronize(s_out));
+  return first_rc;
 }
 
 extern "C" int dp_visibility(dp_context *ctx, dp_patch_soa *h, int32_t *ncand, int32_t *cand) {

@@ -64,6 +64,8 @@ struct DpOrganizer {
 struct dp_context {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream_in = nullptr, stream_out = nullptr;  // copy streams of dp_filter_refine's pipeline
+  std::vector<cudaEvent_t> pipe_events;
   dp_params prm;
   std::vector<DpViewHost> views;
   DpDevBuf d_views;      // DpViewDev[n_views] of the active level

@@ -145,6 +145,36 @@ def test_refine_vs_oracle(c1, exact_orc, s, n):
     assert evals.min() >= 4 and evals.max() <= 503
 
 
+@pytest.mark.parametrize("s", [2, 3, 4, 6, 8])
+def test_group_kernels_every_small_cell(c1, exact_orc, s):
+    """Cells up to 8x8 run the several-patches-per-warp kernels (dp_group.cuh), one template
+    instance per number of texel passes: every size, batch sizes that do not fill the last
+    warp, masked refinement."""
+    d = c1
+    sd = d["seeds"]
+    for n in (1, 7, 203):
+        sl = slice(11, 11 + n)
+        a = (sd["pos"][sl], sd["nrm"][sl], sd["ref"][sl], d["nvis"][sl], d["vis"][sl])
+        ncc, tex, valid = d["ctx"].score(*a, s, want_tex=True)
+        o_ncc, o_tex, o_valid = exact_orc.score_batch(d["V"], *a, s, want_tex=True)
+        assert np.array_equal(valid, o_valid) and np.array_equal(tex, o_tex)
+        assert np.abs(ncc - o_ncc).max() < 1e-6
+        keep, nvis, vis = d["ctx"].filter(*a, s)
+        o_keep, o_nvis, o_vis = exact_orc.filter_batch(d["V"], *a, s, 0.6, 2)
+        assert np.array_equal(keep, o_keep) and np.array_equal(nvis, o_nvis)
+        assert np.array_equal(vis, o_vis)
+    n = 96
+    sl = slice(0, n)
+    a = (sd["pos"][sl], sd["nrm"][sl], sd["ref"][sl], d["nvis"][sl], d["vis"][sl])
+    mask = (np.arange(n) % 3 != 1).astype(np.uint8)
+    pos, nrm, evals, xb = d["ctx"].refine(*a, s, mask=mask)
+    m = mask.astype(bool)
+    o_pos, o_nrm, o_fc, o_xb = exact_orc.refine_batch(d["V"], *(x[m] for x in a), s)
+    assert np.array_equal(evals[m], o_fc) and (evals[~m] == 0).all()
+    assert np.array_equal(pos[m], o_pos) and np.array_equal(nrm[m], o_nrm)
+    assert np.array_equal(pos[~m], sd["pos"][sl][~m]) and np.array_equal(nrm[~m], sd["nrm"][sl][~m])
+
+
 def test_refine_improves_photoconsistency(c1):
     d = c1
     sd = d["seeds"]

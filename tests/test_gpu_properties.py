@@ -103,3 +103,19 @@ def test_c2_shape_filter_refine_properties(sphere, orc):
         assert np.array_equal(op, p2[idx]) and np.array_equal(on, n2[idx])
     finally:
         orc.set_homography_mode(0)
+
+
+def test_pipelined_filter_refine_equals_separate_calls(sphere):
+    """dp_filter_refine cuts large batches into chunks that flow through copy / compute / copy
+    streams; the result must not depend on the chunking (here 150 000 patches = two chunks, the
+    second one ragged) and must equal filter followed by a masked refine."""
+    sc, seeds, ctx = sphere
+    n = 150_000
+    pos, nrm, ref = seeds["pos"][:n], seeds["nrm"][:n], seeds["ref"][:n]
+    nvis, vis, _, _ = ctx.visibility(pos, nrm, ref)
+    keep, fnvis, fvis, p1, n1, ev1 = ctx.filter_refine(pos, nrm, ref, nvis, vis, 7)
+    k2, nv2, vi2 = ctx.filter(pos, nrm, ref, nvis, vis, 7)
+    p2, n2, ev2, _ = ctx.refine(pos, nrm, ref, nv2, vi2, 7, mask=k2)
+    assert np.array_equal(keep, k2) and np.array_equal(fnvis, nv2) and np.array_equal(fvis, vi2)
+    assert np.array_equal(p1, p2) and np.array_equal(n1, n2) and np.array_equal(ev1, ev2)
+    assert keep[131_072:].any() and ev1[131_072:].max() >= 4      # the second chunk did work
