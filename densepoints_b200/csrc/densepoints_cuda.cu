@@ -391,28 +391,26 @@ static int build_order(dp_context *ctx, const int32_t *nvis, const uint8_t *mask
 }
 
 #ifndef DP_SCORE_GROUP
-#define DP_SCORE_GROUP 1  // cells up to 8x8: several patches per warp (dp_group.cuh)
+#define DP_SCORE_GROUP 1  // cells up to 16x16: several patches per warp (dp_group.cuh)
 #endif
 
 template <bool TEX, bool FILT>
 static int launch_score(dp_context *ctx, const DpScoreArgs &a, int cell_size, cudaStream_t st) {
-  if (DP_SCORE_GROUP && cell_size <= 8) {
+  if (DP_SCORE_GROUP && cell_size <= DP_GROUP_MAX_CELL_SCORE) {
     const int32_t *order = nullptr;
     int rc = build_order(ctx, a.p.nvis, nullptr, a.p.n, st, &order);
     if (rc != DP_OK) return rc;
-    const long long per_cta = (long long)DP_GWARPS * DP_GROUPS;
-    const unsigned grid = (unsigned)((a.p.n + per_cta - 1) / per_cta);
-#define DP_GCASE(S)                                                                             \
-  case S:                                                                                       \
-    dp_score_group_kernel<(S * S + DP_GL - 1) / DP_GL, TEX, FILT><<<grid, DP_GWARPS * 32, 0, st>>>( \
-        a, order);                                                                              \
-    break
-    switch (cell_size) {  // texel passes of a group = ceil(s^2 / DP_GL)
-      DP_GCASE(2); DP_GCASE(3); DP_GCASE(4); DP_GCASE(5); DP_GCASE(6); DP_GCASE(7);
-      default:
-        dp_score_group_kernel<(64 + DP_GL - 1) / DP_GL, TEX, FILT><<<grid, DP_GWARPS * 32, 0, st>>>(
-            a, order);
-        break;
+#define DP_GCASE(S)                                                                        \
+  case S: {                                                                                \
+    using C = DpCfgFor<S>;                                                                 \
+    const long long per_cta = (long long)DP_GWARPS * C::GROUPS;                            \
+    const unsigned grid = (unsigned)((a.p.n + per_cta - 1) / per_cta);                     \
+    dp_score_group_kernel<C, TEX, FILT><<<grid, DP_GWARPS * 32, 0, st>>>(a, order);        \
+  } break
+    switch (cell_size) {
+      DP_GCASE(2); DP_GCASE(3); DP_GCASE(4); DP_GCASE(5); DP_GCASE(6); DP_GCASE(7); DP_GCASE(8);
+      DP_GCASE(9); DP_GCASE(10); DP_GCASE(11); DP_GCASE(12); DP_GCASE(13); DP_GCASE(14);
+      DP_GCASE(15); DP_GCASE(16);
     }
 #undef DP_GCASE
     ++ctx->launches;
@@ -495,19 +493,19 @@ static cudaError_t launch_refine(const DpRefineArgs &a, int sm_count, cudaStream
 }
 
 #ifndef DP_REFINE_GROUP
-#define DP_REFINE_GROUP 1  // cells up to 8x8: four patches per warp (dp_group.cuh)
+#define DP_REFINE_GROUP 1  // cells up to 16x16: several patches per warp (dp_group.cuh)
 #endif
-template <int NP>
+template <typename C>
 static cudaError_t launch_refine_group(const DpRefineArgs &a, int sm_count, cudaStream_t st) {
   int per_sm = 1;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dp_refine_group_kernel<NP>,
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dp_refine_group_kernel<C>,
                                                                 DP_GWARPS * 32, 0);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
-  const long long per_cta = (long long)DP_GWARPS * DP_GROUPS;
+  const long long per_cta = (long long)DP_GWARPS * C::GROUPS;
   long long want = ((long long)a.p.n + per_cta - 1) / per_cta;
   long long grid = std::min<long long>(want, (long long)sm_count * per_sm);
-  dp_refine_group_kernel<NP><<<(unsigned)grid, DP_GWARPS * 32, 0, st>>>(a);
+  dp_refine_group_kernel<C><<<(unsigned)grid, DP_GWARPS * 32, 0, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -532,11 +530,14 @@ extern "C" int dp_refine_dev(dp_context *ctx, dp_patch_dev *p, int cell_size, co
   a.mask = mask;
   if ((rc = build_order(ctx, p->nvis, mask, p->n, st, &a.order)) != DP_OK) return rc;
   cudaError_t e;
-  if (DP_REFINE_GROUP && cell_size <= 8) {
-#define DP_GCASE(S) case S: e = launch_refine_group<(S * S + DP_GL - 1) / DP_GL>(a, ctx->sm_count, st); break
-    switch (cell_size) {  // texel passes of a group = ceil(s^2 / DP_GL)
-      DP_GCASE(2); DP_GCASE(3); DP_GCASE(4); DP_GCASE(5); DP_GCASE(6); DP_GCASE(7);
-      default: e = launch_refine_group<(64 + DP_GL - 1) / DP_GL>(a, ctx->sm_count, st); break;
+  if (DP_REFINE_GROUP && cell_size <= DP_GROUP_MAX_CELL_REFINE) {
+    e = cudaSuccess;
+#define DP_GCASE(S) case S: e = launch_refine_group<DpCfgFor<S>>(a, ctx->sm_count, st); break
+    switch (cell_size) {
+      DP_GCASE(2); DP_GCASE(3); DP_GCASE(4); DP_GCASE(5); DP_GCASE(6); DP_GCASE(7); DP_GCASE(8);
+#if DP_GROUP_MAX_CELL_REFINE > 8
+      DP_GCASE(9); DP_GCASE(10); DP_GCASE(11); DP_GCASE(12);
+#endif
     }
 #undef DP_GCASE
   } else

@@ -1,11 +1,11 @@
-// dp_group.cuh -- refine kernel for small cells (s <= 8): FOUR patches per warp.
+// dp_group.cuh -- score / filter / refine kernels with SEVERAL patches per warp (s <= 16).
 //
 // With one warp per patch (dp_refine_kernel) more than half of the warp instructions of an
 // objective evaluation are not texel work: UnparametrizePatch, the patch frame and the
 // Nelder-Mead state machine are scalar (all 32 lanes compute the same value), the per-view
 // set-up fills 8 lane slots of which ~5 are used, the reductions run over 32 lanes for 49
 // texels, and the texel passes themselves use 49 of 64 lane slots.  Here a patch owns a group
-// of DP_GL = 8 lanes and a warp advances four patches in lockstep:
+// of GL lanes (4 for s <= 8) and a warp advances 32 / GL patches in lockstep:
 //   * scalar work is done once per instruction for four patches;
 //   * the set-up pass handles 2 views of each of the 4 patches (8 slots, all used);
 //   * a 7x7 texture takes 7 passes of 8 lanes (56 slots for 49 texels instead of 64);
@@ -21,18 +21,42 @@
 #pragma once
 #include "dp_kernels.cuh"
 
-#ifndef DP_GL
-#define DP_GL 4                  // lanes per patch (measured: 4 > 8 > 16 on B200 at s = 7)
+// Group geometry per cell size: GL lanes per patch, NP = ceil(s^2 / GL) texel passes, and the
+// staging tile of a group (TW x TH pixels).  Measured on B200 at s = 7: 4 lanes per patch
+// 2.46 G evals/s, 8 lanes 2.31, 16 lanes 2.12; larger cells take wider groups so that the
+// per-lane texel arrays and the tiles stay small.
+template <int GL_, int NP_, int TW_, int TH_>
+struct DpGroupCfg {
+  static constexpr int GL = GL_;            // lanes per patch
+  static constexpr int NP = NP_;            // texel passes
+  static constexpr int TW = TW_, TH = TH_;  // staging tile, pixels (TW a multiple of 4)
+  static constexpr int GROUPS = 32 / GL;    // patches per warp
+  static constexpr int GROUND = GL;         // views per round of a group: one per lane in phase C
+  static constexpr int TSTRIDE = TW * TH + 4;  // +4 words: stagger the groups over the banks
+};
+// s <= 8: 4 lanes, 16x8 tile; s <= 12: 8 lanes, 16x16; s <= 16: 16 lanes, 32x24
+template <int S>
+using DpCfgFor = DpGroupCfg<(S <= 8 ? 4 : (S <= 12 ? 8 : 16)),
+                            (S * S + (S <= 8 ? 4 : (S <= 12 ? 8 : 16)) - 1) / (S <= 8 ? 4 : (S <= 12 ? 8 : 16)),
+                            (S <= 12 ? 16 : 32), (S <= 8 ? 8 : (S <= 12 ? 16 : 24))>;
+// Largest cells served by the group kernels.  Measured on B200, group vs warp-per-patch kernel,
+// ~7 views per patch: s = 11 score +18 %, refine +7 %; s = 16 score +33 %, refine -1 %; with
+// 24-49 views per patch (64-view scene, expansion at s = 11) the refine group kernel is 13 %
+// slower (nothing scalar left to amortise, lockstep over unequal view counts), the score
+// kernel neutral.  Hence: score / filter up to 16, refine up to 8.
+#ifndef DP_GROUP_MAX_CELL_SCORE
+#define DP_GROUP_MAX_CELL_SCORE 16
 #endif
-#define DP_GROUPS (32 / DP_GL)   // patches per warp
+#ifndef DP_GROUP_MAX_CELL_REFINE
+#define DP_GROUP_MAX_CELL_REFINE 8
+#endif
+
 #ifndef DP_GWARPS
-#define DP_GWARPS 4              // warps per CTA of the group kernel
+#define DP_GWARPS 4              // warps per CTA of the group kernels
 #endif
 #ifndef DP_GMINCTA
 #define DP_GMINCTA 4             // resident CTAs per SM asked for (register cap 128)
 #endif
-
-#define DP_GROUND DP_GL          // views per round of a group: one per lane in phase C
 
 struct DpGroupLane {
   int sub;         // lane index inside the group
@@ -42,12 +66,12 @@ struct DpGroupLane {
 };
 
 // Texel coordinates (x, y) come as doubles from a per-CTA table in shared memory: texel
-// sub + DP_GL*j of a lane is one LDS.128 at a constant offset from the lane's base pointer.
+// sub + GL*j of a lane is one LDS.128 at a constant offset from the lane's base pointer.
 
-template <typename T>
+template <int GL, typename T>
 __device__ __forceinline__ T dp_group_sum(T v, unsigned mask) {
 #pragma unroll
-  for (int o = DP_GL / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+  for (int o = GL / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
   return v;
 }
 
@@ -239,12 +263,9 @@ __device__ __forceinline__ void dp_unparametrize_g(const double C[3], const doub
 // requested before texel j is blended (their latency hides behind ~45 instructions of
 // arithmetic), the gray values go to a byte per (pass, lane) in shared memory (they are
 // needed again once the mean is known) and the integer moments accumulate on the fly.
-// Per-group staging tile: DP_GTILE_H rows of DP_GTILE_W pixels, filled with 16-byte cp.async
-// copies (one per row and lane: 4 lanes x 4 pixels).  The window starts at the ROI origin
-// rounded down to 4 pixels (16-byte alignment), the taps carry the 0-3 pixel offset.
-#define DP_GTILE_W 16
-#define DP_GTILE_H 8
-#define DP_GTILE_STRIDE (DP_GTILE_W * DP_GTILE_H + 4)  // +4 words: stagger the groups over the banks
+// Per-group staging tile: TH rows of TW pixels, filled with 16-byte cp.async copies (one per
+// row and 4-pixel piece).  The window starts at the ROI origin rounded down to 4 pixels
+// (16-byte alignment), the taps carry the 0-3 pixel offset.
 #ifndef DP_GROUP_STAGE
 #define DP_GROUP_STAGE 1
 #endif
@@ -268,7 +289,7 @@ struct DpWarpConsts {  // one view, from its set-up record
   int pitch, xmax, ymax;
 };
 
-template <bool STAGED>
+template <bool STAGED, int TW>
 __device__ __forceinline__ void dp_texel_fetch(const DpWarpConsts &c, const double2 xy, DpTaps &t) {
   const double x = xy.x, y = xy.y;
   const double Wd = fma(c.M6, x, fma(c.M7, y, 1.0));
@@ -283,10 +304,10 @@ __device__ __forceinline__ void dp_texel_fetch(const DpWarpConsts &c, const doub
   const int x0 = Xc >> 5, y0 = Yc >> 5;  // INTER_BITS = 5
   t.wx1 = (unsigned)(Xc & 31);
   t.wy1 = (unsigned)(Yc & 31);
-  if (STAGED) {  // c.src = the group's tile (+ column offset), rows of DP_GTILE_W pixels
-    const uint32_t *r0 = c.src + (y0 * DP_GTILE_W + x0);
+  if (STAGED) {  // c.src = the group's tile (+ column offset), rows of TW pixels
+    const uint32_t *r0 = c.src + (y0 * TW + x0);
     t.p00 = r0[0]; t.p01 = r0[1];
-    t.p10 = r0[DP_GTILE_W]; t.p11 = r0[DP_GTILE_W + 1];
+    t.p10 = r0[TW]; t.p11 = r0[TW + 1];
   } else {
     const uint32_t *r0 = c.src + (unsigned)(y0 * c.pitch + x0), *r1 = r0 + c.pitch;
     t.p00 = __ldg(r0); t.p01 = __ldg(r0 + 1);
@@ -318,20 +339,21 @@ __device__ __forceinline__ int dp_texel_blend(const DpTaps &t, uint32_t &Bo, uin
 // view is computed, -5 %.)
 
 // gs: this lane's column of the warp's gray buffer, gs[32 * j] = texel j (0 past the patch).
-template <int NP, bool STAGED, bool WRITE_TEX>
+template <typename C, bool STAGED, bool WRITE_TEX>
 __device__ __forceinline__ void dp_texel_loop(const DpWarpConsts &c, int npx, const double2 *txy,
                                               int sub, uint8_t *gs, unsigned &ma, unsigned &mb,
                                               uint8_t *__restrict__ tex_out) {
+  constexpr int NP = C::NP, GL = C::GL;
   DpTaps cur;
-  dp_texel_fetch<STAGED>(c, txy[0], cur);
+  dp_texel_fetch<STAGED, C::TW>(c, txy[0], cur);
   constexpr int kUnroll = DP_TEXEL_UNROLL;
 #pragma unroll kUnroll
   for (int j = 0; j < NP; ++j) {
     DpTaps nxt = cur;
-    if (j + 1 < NP) dp_texel_fetch<STAGED>(c, txy[DP_GL * (j + 1)], nxt);
+    if (j + 1 < NP) dp_texel_fetch<STAGED, C::TW>(c, txy[GL * (j + 1)], nxt);
     uint32_t B, G, Rr;
     int gray = dp_texel_blend(cur, B, G, Rr);
-    const int i = sub + DP_GL * j;
+    const int i = sub + GL * j;
     gray = (i < npx) ? gray : 0;
     if (WRITE_TEX && i < npx) {
       tex_out[3 * i + 0] = (uint8_t)B;
@@ -349,7 +371,7 @@ __device__ __forceinline__ void dp_texel_loop(const DpWarpConsts &c, int npx, co
 // again (128 patches x 5 views per SM do not stay in L1), and with 8 patches per warp nearly
 // every tap load had at least one lane missing L1; staged, the ROI is requested once, all rows
 // at the same time, and the 4 x NP taps per lane are shared-memory reads.
-template <int NP, bool WRITE_TEX>
+template <typename C, bool WRITE_TEX>
 __device__ __forceinline__ void dp_view_texture_rolled(const DpViewSetup &R, int npx,
                                                        const double2 *txy, uint32_t *tile,
                                                        const DpGroupLane &L, uint8_t *gs,
@@ -364,31 +386,36 @@ __device__ __forceinline__ void dp_view_texture_rolled(const DpViewSetup &R, int
   c.ymax = (R.rh - 1) << 5;
   ma = 0;
   mb = 0;
-#if DP_GROUP_STAGE && DP_GL == 4
+#if DP_GROUP_STAGE
   // image rows are 128-byte aligned, so the pixel offset of the ROI inside its 16-byte
   // quad is visible in the pointer
+  constexpr int PR = C::TW / 4;    // 16-byte pieces per tile row
+  constexpr int RS = C::GL / PR;   // rows copied per step by the group
+  static_assert(PR * RS == C::GL, "tile width / group size");
   const int xoff = (int)((reinterpret_cast<uintptr_t>(R.src) >> 2) & 3u);
-  const int wv = (R.rw + xoff + 3) >> 2;  // 16-byte pieces per row
-  if (wv <= DP_GTILE_W / 4 && R.rh <= DP_GTILE_H) {  // uniform inside the group
+  const int wv = (R.rw + xoff + 3) >> 2;  // 16-byte pieces per ROI row
+  if (wv <= PR && R.rh <= C::TH) {  // uniform inside the group
     __syncwarp(L.mask);  // the previous view's taps are done with the tile
-    if (L.sub < wv) {
-      const uint32_t *g = R.src - xoff + 4 * L.sub;
-      uint32_t *d = tile + 4 * L.sub;
+    const int piece = L.sub % PR, row0 = L.sub / PR;
+    if (piece < wv) {
+      const uint32_t *g = R.src - xoff + 4 * piece;
+      uint32_t *d = tile + 4 * piece;
 #pragma unroll
-      for (int r = 0; r < DP_GTILE_H; ++r)
-        if (r < R.rh) dp_cp_async16(d + r * DP_GTILE_W, g + (size_t)r * R.pitch);
+      for (int r = 0; r < C::TH; r += RS)
+        if (r + row0 < R.rh)
+          dp_cp_async16(d + (r + row0) * C::TW, g + (size_t)(r + row0) * R.pitch);
     }
     dp_cp_async_wait_all();
     __syncwarp(L.mask);
     c.src = tile + xoff;
-    dp_texel_loop<NP, true, WRITE_TEX>(c, npx, txy, L.sub, gs, ma, mb, tex_out);
+    dp_texel_loop<C, true, WRITE_TEX>(c, npx, txy, L.sub, gs, ma, mb, tex_out);
     return;
   }
 #endif
-  dp_texel_loop<NP, false, WRITE_TEX>(c, npx, txy, L.sub, gs, ma, mb, tex_out);
+  dp_texel_loop<C, false, WRITE_TEX>(c, npx, txy, L.sub, gs, ma, mb, tex_out);
 }
 
-// Evaluate the visible views of the warp's patches in lockstep, DP_GROUND views per round:
+// Evaluate the visible views of the warp's patches in lockstep, GROUND views per round:
 //   phase A  set-up of the round's views (one view of each patch per pass)
 //   phase B  per view: stage the ROI, warp the texels, integer moments, NCC numerator
 //   phase C  one view per lane of the group: NCCScore(texture 0, texture k)
@@ -396,7 +423,7 @@ __device__ __forceinline__ void dp_view_texture_rolled(const DpViewSetup &R, int
 // holds the score of the group's view k0 + sub (sub < kc; -1 when either texture is empty,
 // error_measurements.cpp:38-40; the entry of view 0 is meaningless); kcmax is the largest kc in
 // the warp.  nv = 0 marks a group that does not evaluate.  Must be called by the whole warp.
-template <int NP, bool WRITE_TEX, typename Sink>
+template <typename C, bool WRITE_TEX, typename Sink>
 __device__ __forceinline__ void dp_eval_views_g(const DpViewDev *__restrict__ views, int n_views,
                                                 int ref, bool ref_ok, const int32_t *vis, int nv,
                                                 int s, int npx, const double n[3], const double p[3],
@@ -406,17 +433,18 @@ __device__ __forceinline__ void dp_eval_views_g(const DpViewDev *__restrict__ vi
   DpFrame f;
   dp_make_frame(views + (ref_ok ? ref : 0), s, n, p, f);
   if (!ref_ok) f.ok = false;  // every texture empty (optimization.cpp:45)
+  constexpr int NP = C::NP, GL = C::GL, GROUND = C::GROUND;
   const double scale = 1.0 / (double)npx;  // cv::meanStdDev: mean = sum * (1/N)
   float da[NP];                             // centred anchor texels (texture 0)
   unsigned a1 = 0, a2 = 0;
   bool a_ok = false;
   const int nvmax = __reduce_max_sync(DP_FULL, nv);
 #pragma unroll 1
-  for (int k0 = 0; k0 < nvmax; k0 += DP_GROUND) {
-    const int kc = min(max(nv - k0, 0), DP_GROUND);   // this group's views in the round
-    const int kcmax = min(DP_GROUND, nvmax - k0);     // warp-uniform loop bound
+  for (int k0 = 0; k0 < nvmax; k0 += GROUND) {
+    const int kc = min(max(nv - k0, 0), GROUND);   // this group's views in the round
+    const int kcmax = min(GROUND, nvmax - k0);     // warp-uniform loop bound
     __syncwarp();
-    dp_setup_views<DP_GL>(views, n_views, vis + k0, kc, kcmax, s, f, recs, lane, false);
+    dp_setup_views<GL>(views, n_views, vis + k0, kc, kcmax, s, f, recs, lane, false);
     __syncwarp();
     unsigned my1 = 0, my2 = 0;
     double mynum = 0.0;
@@ -429,11 +457,11 @@ __device__ __forceinline__ void dp_eval_views_g(const DpViewDev *__restrict__ vi
       double num = 0.0;
       if (ok) {
         unsigned ma = 0, mb = 0;
-        dp_view_texture_rolled<NP, WRITE_TEX>(
+        dp_view_texture_rolled<C, WRITE_TEX>(
             R, npx, txy, tile, L, gs, ma, mb,
             WRITE_TEX ? tex_base + (size_t)(k0 + l) * npx * 3 : nullptr);
-        s1 = dp_group_sum(ma, L.mask);  // exact integer moments (cv::meanStdDev's sums)
-        s2 = dp_group_sum(mb, L.mask);
+        s1 = dp_group_sum<GL>(ma, L.mask);  // exact integer moments (cv::meanStdDev's sums)
+        s2 = dp_group_sum<GL>(mb, L.mask);
         // fl32(g_i - fl32(mean)): `Mat - scalar` on CV_32F (error_measurements.cpp:54); the
         // lane reads back its own column of the gray buffer: no barrier needed
         const float mf = (float)xmul((double)s1, scale);
@@ -443,14 +471,14 @@ __device__ __forceinline__ void dp_eval_views_g(const DpViewDev *__restrict__ vi
           a_ok = true;
 #pragma unroll
           for (int j = 0; j < NP; ++j)
-            da[j] = (L.sub + DP_GL * j < npx) ? __fsub_rn((float)gs[32 * j], mf) : 0.f;
+            da[j] = (L.sub + GL * j < npx) ? __fsub_rn((float)gs[32 * j], mf) : 0.f;
         } else if (a_ok) {
 #pragma unroll
           for (int j = 0; j < NP; ++j) {
-            const float db = (L.sub + DP_GL * j < npx) ? __fsub_rn((float)gs[32 * j], mf) : 0.f;
+            const float db = (L.sub + GL * j < npx) ? __fsub_rn((float)gs[32 * j], mf) : 0.f;
             num = xadd(num, xmul((double)da[j], (double)db));
           }
-          num = dp_group_sum(num, L.mask);
+          num = dp_group_sum<GL>(num, L.mask);
         }
       }
       if (L.sub == l) {
@@ -471,7 +499,7 @@ __device__ __forceinline__ void dp_eval_views_g(const DpViewDev *__restrict__ vi
 
 // PatchOptimizationOpenCVFunctor::calc for all patches of the warp at once: mean of (1 - NCC)
 // over the visible views in view order (optimization_opencv.cpp:17-35).
-template <int NP>
+template <typename C>
 __device__ __forceinline__ double dp_objective_g(const DpViewDev *__restrict__ views, int n_views,
                                                  int ref, const int32_t *vis, int nv, int s, int npx,
                                                  const double n[3], const double p[3],
@@ -479,7 +507,7 @@ __device__ __forceinline__ double dp_objective_g(const DpViewDev *__restrict__ v
                                                  uint8_t *gs, uint32_t *tile, int lane,
                                                  const DpGroupLane &L) {
   double sum = 0.0;
-  dp_eval_views_g<NP, false>(
+  dp_eval_views_g<C, false>(
       views, n_views, ref, true, vis, nv, s, npx, n, p, recs, txy, gs, tile, lane, L, nullptr, nullptr,
       [&](int k0, int kc, int kcmax, double score) {
         // std::accumulate of (1 - NCC) in view order (optimization_opencv.cpp:24, 34)
@@ -493,49 +521,51 @@ __device__ __forceinline__ double dp_objective_g(const DpViewDev *__restrict__ v
 }
 
 // Shared memory of a CTA of the group kernels.
-template <int NP>
+template <typename C>
 struct DpGroupShared {
-  DpViewSetup recs[DP_GWARPS][DP_GROUPS][DP_GROUND];
-  double2 txy[NP * DP_GL];
+  DpViewSetup recs[DP_GWARPS][C::GROUPS][C::GROUND];
+  double2 txy[C::NP * C::GL];
   // +32 words: the neighbour taps of an edge pixel (weight 0) may read past the last tile
-  __align__(16) uint32_t tile[DP_GROUP_STAGE ? DP_GWARPS * DP_GROUPS * DP_GTILE_STRIDE + 32 : 4];
-  uint8_t gray[DP_GWARPS][NP][32];
+  __align__(16) uint32_t tile[DP_GROUP_STAGE ? DP_GWARPS * C::GROUPS * C::TSTRIDE + 32 : 4];
+  uint8_t gray[DP_GWARPS][C::NP][32];
   __device__ __forceinline__ void init_texels(int s, int npx) {
-    for (int t = threadIdx.x; t < NP * DP_GL; t += blockDim.x) {
+    for (int t = threadIdx.x; t < C::NP * C::GL; t += blockDim.x) {
       const int tt = t < npx ? t : 0;  // lanes past the last texel work on texel 0, masked later
       const int yy = tt / s;
       txy[t] = make_double2((double)(tt - yy * s), (double)yy);
     }
   }
   __device__ __forceinline__ uint32_t *group_tile(int warp, int grp) {
-    return tile + (DP_GROUP_STAGE ? (warp * DP_GROUPS + grp) * DP_GTILE_STRIDE : 0);
+    return tile + (DP_GROUP_STAGE ? (warp * C::GROUPS + grp) * C::TSTRIDE : 0);
   }
 };
 
+template <int GL>
 __device__ __forceinline__ DpGroupLane dp_group_lane(int lane) {
   DpGroupLane L;
-  L.sub = lane & (DP_GL - 1);
-  L.base = lane & ~(DP_GL - 1);
-  L.mask = (DP_GL == 32) ? DP_FULL : (((1u << DP_GL) - 1u) << L.base);
+  L.sub = lane & (GL - 1);
+  L.base = lane & ~(GL - 1);
+  L.mask = (GL == 32) ? DP_FULL : (((1u << GL) - 1u) << L.base);
   L.leader = L.sub == 0;
   return L;
 }
 
-// K1+K2 for cells up to 8x8: GetProjectedTextures + NCCScore for every visible view and,
+// K1+K2 for cells up to 16x16: GetProjectedTextures + NCCScore for every visible view and,
 // fused, FilterByErrorMeasurement's erase loop -- the warp-per-patch dp_score_kernel with
-// DP_GROUPS patches per warp.  Work item `slot` = patch order[slot] (patches sorted by view
+// C::GROUPS patches per warp.  Work item `slot` = patch order[slot] (patches sorted by view
 // count so that the patches of a warp run the same number of view steps), or patch `slot`.
-template <int NP, bool WRITE_TEX, bool FILTER>
+template <typename C, bool WRITE_TEX, bool FILTER>
 __global__ void __launch_bounds__(DP_GWARPS * 32, DP_GMINCTA)
 dp_score_group_kernel(DpScoreArgs a, const int32_t *__restrict__ order) {
-  __shared__ DpGroupShared<NP> sh;
+  constexpr int GL = C::GL;
+  __shared__ DpGroupShared<C> sh;
   const int s = a.p.s, npx = s * s;
   sh.init_texels(s, npx);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const DpGroupLane L = dp_group_lane(lane);
-  const int grp = lane / DP_GL;
-  const long long slot = ((long long)blockIdx.x * DP_GWARPS + warp) * DP_GROUPS + grp;
+  const DpGroupLane L = dp_group_lane<GL>(lane);
+  const int grp = lane / GL;
+  const long long slot = ((long long)blockIdx.x * DP_GWARPS + warp) * C::GROUPS + grp;
   const bool have = slot < a.p.n;
   const long long i = have ? (order ? (long long)order[slot] : slot) : 0;
   const int nv = have ? min(a.p.nvis[i], a.p.vstride) : 0;
@@ -550,7 +580,7 @@ dp_score_group_kernel(DpScoreArgs a, const int32_t *__restrict__ order) {
   int wcur = 0;
   const double thr = a.thr;
   const unsigned lt = (1u << L.sub) - 1u;
-  dp_eval_views_g<NP, WRITE_TEX>(
+  dp_eval_views_g<C, WRITE_TEX>(
       a.p.views, a.p.n_views, ref, ref_ok, vis, nv, s, npx, n, p,
       sh.recs[warp][grp], sh.txy + L.sub, &sh.gray[warp][0][lane], sh.group_tile(warp, grp), lane, L,
       tex, valid, [&](int k0, int kc, int kcmax, double score) {
@@ -562,7 +592,7 @@ dp_score_group_kernel(DpScoreArgs a, const int32_t *__restrict__ order) {
           // compacted in place with the group's bits of a warp ballot
           const bool keepf = mine && !(score < thr);
           const int prev = mine ? vis[k - 1] : -1;
-          const unsigned m = (__ballot_sync(DP_FULL, keepf) >> L.base) & ((1u << DP_GL) - 1u);
+          const unsigned m = (__ballot_sync(DP_FULL, keepf) >> L.base) & ((GL == 32) ? DP_FULL : ((1u << GL) - 1u));
           __syncwarp();
           if (keepf) vis[wcur + __popc(m & lt)] = prev;
           wcur += __popc(m);
@@ -575,7 +605,7 @@ dp_score_group_kernel(DpScoreArgs a, const int32_t *__restrict__ order) {
       if (L.leader) vis[wcur] = vis[nv - 1];
       ++wcur;
       __syncwarp(L.mask);
-      for (int k = wcur + L.sub; k < nv; k += DP_GL) vis[k] = -1;
+      for (int k = wcur + L.sub; k < nv; k += GL) vis[k] = -1;
       if (L.leader) a.p.nvis[i] = wcur;
       kept = wcur >= a.min_visible;  // optimization.cpp:127
     }
@@ -583,15 +613,16 @@ dp_score_group_kernel(DpScoreArgs a, const int32_t *__restrict__ order) {
   }
 }
 
-template <int NP>
+template <typename C>
 __global__ void __launch_bounds__(DP_GWARPS * 32, DP_GMINCTA) dp_refine_group_kernel(DpRefineArgs a) {
-  __shared__ DpGroupShared<NP> sh;
-  __shared__ DpNelderMead nm_s[DP_GWARPS][DP_GROUPS];
+  constexpr int GL = C::GL;
+  __shared__ DpGroupShared<C> sh;
+  __shared__ DpNelderMead nm_s[DP_GWARPS][C::GROUPS];
   const int s = a.p.s, npx = s * s;
   sh.init_texels(s, npx);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const DpGroupLane L = dp_group_lane(lane);
-  const int grp = lane / DP_GL;
+  const DpGroupLane L = dp_group_lane<GL>(lane);
+  const int grp = lane / GL;
   DpViewSetup *recs = sh.recs[warp][grp];
   DpNelderMead &S = nm_s[warp][grp];
   if (L.leader) {  // defined values for the lockstep evaluations of a group without a patch
@@ -663,7 +694,7 @@ __global__ void __launch_bounds__(DP_GWARPS * 32, DP_GMINCTA) dp_refine_group_ke
       dp_unparametrize_g(c3, n0, p0, S.pt[0], S.pt[1], S.pt[2], n, p, L, DP_FULL);
     }
     const int nv_eval = (have && nv >= 2 && ref_ok) ? nv : 0;
-    const double fobj = dp_objective_g<NP>(a.p.views, a.p.n_views, ref_ok ? ref : 0, vis, nv_eval, s,
+    const double fobj = dp_objective_g<C>(a.p.views, a.p.n_views, ref_ok ? ref : 0, vis, nv_eval, s,
                                            npx, n, p, recs, txy, &sh.gray[warp][0][lane],
                                            sh.group_tile(warp, grp), lane, L);
     const double fval = nv_eval ? fobj : 2.0;  // scores.size() == 0 (optimization_opencv.cpp:30-32)

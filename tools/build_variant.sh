@@ -8,5 +8,5 @@ mkdir -p "$ROOT/densepoints_b200/_variants"
 cd "$ROOT/densepoints_b200/csrc"
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC "$@" \
   -Xptxas -v -o "$ROOT/densepoints_b200/_variants/$name.so" densepoints_cuda.cu 2>&1 \
-  | grep -A2 "dp_refine_group_kernelILi13E\|dp_refine_group_kernelILi7E\|dp_score_kernelILi2ELb0ELb1" | grep "spill\|Used" | tr '\n' ' '
+  | grep -A2 "dp_refine_group_kernelI10DpGroupCfgILi4ELi13E\|dp_refine_group_kernelI10DpGroupCfgILi8ELi16E" | grep "spill\|Used" | tr '\n' ' '
 echo " <- $name"
