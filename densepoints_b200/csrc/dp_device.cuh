@@ -300,9 +300,6 @@ __device__ __forceinline__ void dp_setup_views(const DpViewDev *__restrict__ vie
 
 // Generic staging: tile rows padded to a power-of-two pitch so the flat index splits with a
 // shift and a mask; each 32-lane step loads 32/pitch whole rows with 32-bit loads.
-#ifndef DP_STAGE_FAST
-#define DP_STAGE_FAST 1
-#endif
 template <int NFAST>
 __device__ __forceinline__ bool dp_stage_roi(const DpViewSetup &R, uint32_t *tile, int tile_cap,
                                              int lane) {
@@ -311,7 +308,6 @@ __device__ __forceinline__ bool dp_stage_roi(const DpViewSetup &R, uint32_t *til
   if (area > tile_cap) return false;
   const uint32_t *__restrict__ src = R.src;
   const int cmask = (1 << lgp) - 1;
-#if DP_STAGE_FAST
   // The first 32*NFAST tile entries (the whole ROI in the normal case) without a branch: all
   // loads are issued before the first store, lanes past the ROI load nothing and store 0.
   uint32_t v[NFAST];
@@ -328,12 +324,6 @@ __device__ __forceinline__ bool dp_stage_roi(const DpViewSetup &R, uint32_t *til
       const int r = t >> lgp, c = t & cmask;
       if (c < rw) tile[t] = __ldg(src + (unsigned)(r * pitch + c));
     }
-#else
-  for (int t = lane; t < area; t += 32) {
-    const int r = t >> lgp, c = t & cmask;
-    if (c < rw) tile[t] = __ldg(src + (unsigned)(r * pitch + c));
-  }
-#endif
   __syncwarp();
   return true;
 }
@@ -355,9 +345,6 @@ __device__ __forceinline__ void dp_view_texture(const DpViewSetup &R, int npx, c
 #pragma unroll
   for (int j = 0; j < NPASS; ++j) {
     const int i = lane + GL * j;
-#ifdef DP_ABL_ONEPASS  // ablation (wrong results): only the first texel pass is computed
-    if (j > 0) { g[j] = g[0]; continue; }
-#endif
     double x, y;
     tx.get(j, i, x, y);
     const double Wd = fma(M6, x, fma(M7, y, 1.0));

@@ -1,23 +1,25 @@
 // dp_group.cuh -- score / filter / refine kernels with SEVERAL patches per warp (s <= 16).
 //
-// With one warp per patch (dp_refine_kernel) more than half of the warp instructions of an
+// With one warp per patch (dp_kernels.cuh) more than half of the warp instructions of an
 // objective evaluation are not texel work: UnparametrizePatch, the patch frame and the
 // Nelder-Mead state machine are scalar (all 32 lanes compute the same value), the per-view
 // set-up fills 8 lane slots of which ~5 are used, the reductions run over 32 lanes for 49
 // texels, and the texel passes themselves use 49 of 64 lane slots.  Here a patch owns a group
 // of GL lanes (4 for s <= 8) and a warp advances 32 / GL patches in lockstep:
-//   * scalar work is done once per instruction for four patches;
-//   * the set-up pass handles 2 views of each of the 4 patches (8 slots, all used);
-//   * a 7x7 texture takes 7 passes of 8 lanes (56 slots for 49 texels instead of 64);
-//   * reductions are 3-step shuffle trees inside the group.
-// The warp's control flow stays uniform: every iteration of the main loop is one objective
-// evaluation for each of the four patches (at its own simplex point), the view loop runs to
-// the largest view count in the warp (patches are handed out sorted by view count, so the
-// four usually agree), and only the short Nelder-Mead bookkeeping diverges per group.  A group
-// whose patch has converged writes it back and takes the next patch from the work counter.
+//   * scalar work is done once per instruction for 8 patches;
+//   * a set-up pass handles one view of each of the 8 patches (4 corners x 8 slots, all used);
+//   * a 7x7 texture takes 13 passes of 4 lanes (52 slots for 49 texels instead of 64);
+//   * reductions are 2-step shuffle trees inside the group.
+// The warp's control flow stays uniform: every iteration of the refine kernel's main loop is
+// one objective evaluation for each of the warp's patches (at its own simplex point), the view
+// loop runs to the largest view count in the warp (patches are handed out sorted by view
+// count, so they usually agree), and only the short Nelder-Mead bookkeeping diverges per
+// group.  A group whose patch has converged writes it back and takes the next patch from the
+// work counter.
 //
 // The arithmetic is the one of dp_kernels.cuh / dp_device.cuh (same functions); only the
-// order of the fp64 partial sums of the NCC numerator differs (8-lane tree), ~1e-16.
+// order of the fp64 partial sums of the NCC numerator differs (group tree), ~1e-16: scores,
+// keep bits, visible sets, evaluation counts and refined fp32 geometry are bit-identical.
 #pragma once
 #include "dp_kernels.cuh"
 

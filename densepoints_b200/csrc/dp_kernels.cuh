@@ -25,11 +25,6 @@ __host__ __device__ constexpr int dp_score_min_ctas(int npass) {
 #endif
 __host__ __device__ constexpr int dp_refine_min_ctas(int npass) { return npass <= 8 ? DP_RMINCTA : 1; }
 
-// Tuning switches (tools/build_variant.sh).
-#ifndef DP_REFINE_DIRECT
-#define DP_REFINE_DIRECT 1  // refine kernel: no staging, bilinear taps straight from global / L1
-#endif
-
 struct DpPatchArgs {
   const DpViewDev *views;
   int n_views;
@@ -64,7 +59,7 @@ struct DpScoreArgs {
 template <int NPASS, bool TMA>
 struct DpTileCfg {
   static constexpr bool kTma = TMA && NPASS <= 4;
-  static constexpr bool kDirect = !TMA && (DP_REFINE_DIRECT != 0);
+  static constexpr bool kDirect = !TMA;
   static constexpr int kTilePx =
       kDirect ? 1 : (kTma ? DP_TMA_BOX * DP_TMA_BOX : (128 * NPASS < 768 ? 128 * NPASS : 768));
   static constexpr int kBufs = kTma ? 2 : 1;
@@ -117,14 +112,7 @@ __device__ __forceinline__ void dp_eval_views(const DpViewDev *__restrict__ view
   for (int k0 = 0; k0 < nv; k0 += DP_ROUND) {
     const int kc = min(DP_ROUND, nv - k0);
     __syncwarp();
-#ifdef DP_ABL_NOSETUP  // ablation (wrong results): set-up only once per patch
-    if (!(phase & 0x80000000u)) {
-      dp_setup_views<32>(views, n_views, vis + k0, kc, kc, s, f, recs, lane, kTma);
-      phase |= 0x80000000u;
-    }
-#else
     dp_setup_views<32>(views, n_views, vis + k0, kc, kc, s, f, recs, lane, kTma);
-#endif
     __syncwarp();
     if (kTma && lane == 0 && recs[0].ok && recs[0].tmap != nullptr)  // first box of the round
       dp_tma_load_tile(ws.tile[0], recs[0].tmap, recs[0].tlx, recs[0].tly, &ws.bar[0]);
@@ -150,12 +138,8 @@ __device__ __forceinline__ void dp_eval_views(const DpViewDev *__restrict__ view
           phase ^= 1u << b;
           staged = true;
         } else if (!DpTileCfg<NPASS, TMA>::kDirect) {
-#ifdef DP_ABL_NOSTAGE  // ablation (wrong results): texels read whatever the tile holds
-          staged = true;
-#else
           staged = dp_stage_roi<(NPASS < 4 ? NPASS : 4)>(R, ws.tile[b],
                                                          DpTileCfg<NPASS, TMA>::kTilePx, lane);
-#endif
         }
         int g[NPASS];
         uint8_t *tex_out = WRITE_TEX ? tex_base + (size_t)(k0 + l) * npx * 3 : nullptr;
@@ -421,9 +405,6 @@ __global__ void __launch_bounds__(DP_RWARPS * 32, dp_refine_min_ctas(NPASS)) dp_
       if (a.evals && lane == 0) a.evals[i] = 0;
       continue;
     }
-#ifdef DP_ABL_NOSETUP
-    phase = 0;
-#endif
     const int nv = min(a.p.nvis[i], a.p.vstride);
     const int ref = a.p.ref[i];
     const bool ref_ok = ref >= 0 && ref < a.p.n_views;
