@@ -333,7 +333,7 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak,
                 "traffic": cap["dram_bytes_per_launch"] if cap else None,
-                "kernel": cap["kernel"] if cap else "dp_refine_group_kernel<13>",
+                "kernel": cap["kernel"] if cap else "dp_refine_group_kernel<DpGroupCfg<4, 13, 16, 8>>",
                 "kernel_ms": refine_kernel_ms, "peak_source": peak_src,
                 "alg_bytes_per_eval": b_alg(CELL, mean_nv), "alg_bytes_per_launch": alg_bytes,
                 "share_of_step": refine_kernel_ms * args.steps / gpu_ms,
