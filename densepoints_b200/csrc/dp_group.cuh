@@ -373,11 +373,44 @@ __device__ __forceinline__ void dp_texel_loop(const DpWarpConsts &c, int npx, co
 // again (128 patches x 5 views per SM do not stay in L1), and with 8 patches per warp nearly
 // every tap load had at least one lane missing L1; staged, the ROI is requested once, all rows
 // at the same time, and the 4 x NP taps per lane are shared-memory reads.
+// (Measured and rejected: requesting the next view's ROI right after the texel loop of the
+// current view, so that its latency hides behind the reductions: -6 %.)
+
+// Requests the ROI of one view into the group's tile; false when it does not fit the tile (the
+// taps then come straight from global memory).  The caller has made sure that the group is done
+// reading the tile.  Completion: dp_cp_async_wait_all() + __syncwarp(group).
+template <typename C>
+__device__ __forceinline__ bool dp_stage_issue(const DpViewSetup &R, uint32_t *tile,
+                                               const DpGroupLane &L) {
+#if DP_GROUP_STAGE
+  constexpr int PR = C::TW / 4;    // 16-byte pieces per tile row
+  constexpr int RS = C::GL / PR;   // rows copied per step by the group
+  static_assert(PR * RS == C::GL, "tile width / group size");
+  // image rows are 128-byte aligned, so the pixel offset of the ROI inside its 16-byte
+  // quad is visible in the pointer
+  const int xoff = (int)((reinterpret_cast<uintptr_t>(R.src) >> 2) & 3u);
+  const int wv = (R.rw + xoff + 3) >> 2;  // 16-byte pieces per ROI row
+  if (wv > PR || R.rh > C::TH) return false;  // uniform inside the group
+  const int piece = L.sub % PR, row0 = L.sub / PR;
+  if (piece < wv) {
+    const uint32_t *g = R.src - xoff + 4 * piece;
+    uint32_t *d = tile + 4 * piece;
+#pragma unroll
+    for (int r = 0; r < C::TH; r += RS)
+      if (r + row0 < R.rh)
+        dp_cp_async16(d + (r + row0) * C::TW, g + (size_t)(r + row0) * R.pitch);
+  }
+  return true;
+#else
+  return false;
+#endif
+}
+
 template <typename C, bool WRITE_TEX>
 __device__ __forceinline__ void dp_view_texture_rolled(const DpViewSetup &R, int npx,
                                                        const double2 *txy, uint32_t *tile,
-                                                       const DpGroupLane &L, uint8_t *gs,
-                                                       unsigned &ma, unsigned &mb,
+                                                       bool staged, const DpGroupLane &L,
+                                                       uint8_t *gs, unsigned &ma, unsigned &mb,
                                                        uint8_t *__restrict__ tex_out) {
   DpWarpConsts c;
   c.M0 = R.M[0]; c.M1 = R.M[1]; c.M2 = R.M[2]; c.M3 = R.M[3];
@@ -388,33 +421,14 @@ __device__ __forceinline__ void dp_view_texture_rolled(const DpViewSetup &R, int
   c.ymax = (R.rh - 1) << 5;
   ma = 0;
   mb = 0;
-#if DP_GROUP_STAGE
-  // image rows are 128-byte aligned, so the pixel offset of the ROI inside its 16-byte
-  // quad is visible in the pointer
-  constexpr int PR = C::TW / 4;    // 16-byte pieces per tile row
-  constexpr int RS = C::GL / PR;   // rows copied per step by the group
-  static_assert(PR * RS == C::GL, "tile width / group size");
-  const int xoff = (int)((reinterpret_cast<uintptr_t>(R.src) >> 2) & 3u);
-  const int wv = (R.rw + xoff + 3) >> 2;  // 16-byte pieces per ROI row
-  if (wv <= PR && R.rh <= C::TH) {  // uniform inside the group
-    __syncwarp(L.mask);  // the previous view's taps are done with the tile
-    const int piece = L.sub % PR, row0 = L.sub / PR;
-    if (piece < wv) {
-      const uint32_t *g = R.src - xoff + 4 * piece;
-      uint32_t *d = tile + 4 * piece;
-#pragma unroll
-      for (int r = 0; r < C::TH; r += RS)
-        if (r + row0 < R.rh)
-          dp_cp_async16(d + (r + row0) * C::TW, g + (size_t)(r + row0) * R.pitch);
-    }
+  if (staged) {
     dp_cp_async_wait_all();
     __syncwarp(L.mask);
-    c.src = tile + xoff;
+    c.src = tile + (int)((reinterpret_cast<uintptr_t>(R.src) >> 2) & 3u);
     dp_texel_loop<C, true, WRITE_TEX>(c, npx, txy, L.sub, gs, ma, mb, tex_out);
-    return;
+  } else {
+    dp_texel_loop<C, false, WRITE_TEX>(c, npx, txy, L.sub, gs, ma, mb, tex_out);
   }
-#endif
-  dp_texel_loop<C, false, WRITE_TEX>(c, npx, txy, L.sub, gs, ma, mb, tex_out);
 }
 
 // Evaluate the visible views of the warp's patches in lockstep, GROUND views per round:
@@ -459,8 +473,10 @@ __device__ __forceinline__ void dp_eval_views_g(const DpViewDev *__restrict__ vi
       double num = 0.0;
       if (ok) {
         unsigned ma = 0, mb = 0;
+        __syncwarp(L.mask);  // the previous view's taps are done with the tile
+        const bool staged = dp_stage_issue<C>(R, tile, L);
         dp_view_texture_rolled<C, WRITE_TEX>(
-            R, npx, txy, tile, L, gs, ma, mb,
+            R, npx, txy, tile, staged, L, gs, ma, mb,
             WRITE_TEX ? tex_base + (size_t)(k0 + l) * npx * 3 : nullptr);
         s1 = dp_group_sum<GL>(ma, L.mask);  // exact integer moments (cv::meanStdDev's sums)
         s2 = dp_group_sum<GL>(mb, L.mask);
