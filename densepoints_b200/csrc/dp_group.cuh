@@ -295,8 +295,10 @@ template <bool STAGED, int TW>
 __device__ __forceinline__ void dp_texel_fetch(const DpWarpConsts &c, const double2 xy, DpTaps &t) {
   const double x = xy.x, y = xy.y;
   const double Wd = fma(c.M6, x, fma(c.M7, y, 1.0));
-  double r = dp_rcp(Wd);
-  r = (Wd != 0.0) ? r : 0.0;  // W ? INTER_TAB_SIZE / W : 0
+  // W ? INTER_TAB_SIZE / W : 0 -- without a select: W == 0 makes r (inf, then NaN after the
+  // Newton steps), fX and fY NaN, and cvt.rni.s32.f64 turns NaN into 0 = what the reference's
+  // zero scale gives (the numerators are finite, dp_setup_views checks the map)
+  const double r = dp_rcp(Wd);
   const double fX = fma(c.M0, x, fma(c.M1, y, c.M2)) * r;
   const double fY = fma(c.M3, x, fma(c.M4, y, c.M5)) * r;
   const int Xi = __double2int_rn(fX);  // saturate_cast<int>(cvRound), half to even
@@ -322,8 +324,11 @@ __device__ __forceinline__ int dp_texel_blend(const DpTaps &t, uint32_t &Bo, uin
   const uint32_t wx1 = t.wx1, wx0 = 32u - wx1, wy1 = t.wy1, wy0 = 32u - wy1;
   const uint32_t br0 = (t.p00 & 0x00ff00ffu) * wx0 + (t.p01 & 0x00ff00ffu) * wx1;  // B | R<<16
   const uint32_t br1 = (t.p10 & 0x00ff00ffu) * wx0 + (t.p11 & 0x00ff00ffu) * wx1;
-  const uint32_t g0 = (t.p00 & 0xff00u) * wx0 + (t.p01 & 0xff00u) * wx1;  // G << 8
-  const uint32_t g1 = (t.p10 & 0xff00u) * wx0 + (t.p11 & 0xff00u) * wx1;
+  // G << 8 = the blend of the whole pixel word minus its B | R part: the x byte of a pixel is 0
+  // and every partial sum is <= 255 * 32, so the word blend is < 2^30 and the difference is
+  // exact (two masks less per tap pair).  A tap with weight 0 may be any word.
+  const uint32_t g0 = (t.p00 * wx0 + t.p01 * wx1) - br0;
+  const uint32_t g1 = (t.p10 * wx0 + t.p11 * wx1) - br1;
   const uint32_t B = ((br0 & 0xffffu) * wy0 + (br1 & 0xffffu) * wy1 + 512u) >> 10;
   const uint32_t Rr = ((br0 >> 16) * wy0 + (br1 >> 16) * wy1 + 512u) >> 10;
   const uint32_t G = (g0 * wy0 + g1 * wy1 + (512u << 8)) >> 18;
@@ -349,23 +354,40 @@ __device__ __forceinline__ void dp_texel_loop(const DpWarpConsts &c, int npx, co
   DpTaps cur;
   dp_texel_fetch<STAGED, C::TW>(c, txy[0], cur);
   constexpr int kUnroll = DP_TEXEL_UNROLL;
+  // passes 0 .. NP-2 hold texels of the patch in every lane (GL * (NP - 1) < npx); only the last
+  // pass needs the mask and it has nothing to prefetch, so it is peeled off the loop
 #pragma unroll kUnroll
-  for (int j = 0; j < NP; ++j) {
-    DpTaps nxt = cur;
-    if (j + 1 < NP) dp_texel_fetch<STAGED, C::TW>(c, txy[GL * (j + 1)], nxt);
+  for (int j = 0; j < NP - 1; ++j) {
+    txy += GL;
+    DpTaps nxt;
+    dp_texel_fetch<STAGED, C::TW>(c, txy[0], nxt);
+    uint32_t B, G, Rr;
+    const int gray = dp_texel_blend(cur, B, G, Rr);
+    if (WRITE_TEX) {
+      const int i = sub + GL * j;
+      tex_out[3 * i + 0] = (uint8_t)B;
+      tex_out[3 * i + 1] = (uint8_t)G;
+      tex_out[3 * i + 2] = (uint8_t)Rr;
+    }
+    *gs = (uint8_t)gray;
+    gs += 32;
+    ma += (unsigned)gray;
+    mb += (unsigned)(gray * gray);
+    cur = nxt;
+  }
+  {
     uint32_t B, G, Rr;
     int gray = dp_texel_blend(cur, B, G, Rr);
-    const int i = sub + GL * j;
+    const int i = sub + GL * (NP - 1);
     gray = (i < npx) ? gray : 0;
     if (WRITE_TEX && i < npx) {
       tex_out[3 * i + 0] = (uint8_t)B;
       tex_out[3 * i + 1] = (uint8_t)G;
       tex_out[3 * i + 2] = (uint8_t)Rr;
     }
-    gs[32 * j] = (uint8_t)gray;
+    *gs = (uint8_t)gray;
     ma += (unsigned)gray;
     mb += (unsigned)(gray * gray);
-    cur = nxt;
   }
 }
 
@@ -487,14 +509,17 @@ __device__ __forceinline__ void dp_eval_views_g(const DpViewDev *__restrict__ vi
           a1 = s1;
           a2 = s2;
           a_ok = true;
+          // only the last pass can hold texels past the patch (GL * (NP - 1) < npx)
 #pragma unroll
           for (int j = 0; j < NP; ++j)
-            da[j] = (L.sub + GL * j < npx) ? __fsub_rn((float)gs[32 * j], mf) : 0.f;
+            da[j] = (j < NP - 1 || L.sub + GL * j < npx) ? __fsub_rn((float)gs[32 * j], mf) : 0.f;
         } else if (a_ok) {
 #pragma unroll
           for (int j = 0; j < NP; ++j) {
-            const float db = (L.sub + GL * j < npx) ? __fsub_rn((float)gs[32 * j], mf) : 0.f;
-            num = xadd(num, xmul((double)da[j], (double)db));
+            const float db = (j < NP - 1 || L.sub + GL * j < npx) ? __fsub_rn((float)gs[32 * j], mf) : 0.f;
+            // the product of two floats is exact in fp64, so the fused form rounds exactly
+            // like num + da * db
+            num = fma((double)da[j], (double)db, num);
           }
           num = dp_group_sum<GL>(num, L.mask);
         }

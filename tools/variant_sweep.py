@@ -2,7 +2,13 @@
 GPU): filter + refine on the bench workload shape.  The first library is the reference for a
 bit-equality check of the outputs (ablation builds are expected to differ).
 
-usage: python tools/variant_sweep.py [--seeds N] [--full-res] [--reps R] [--cell S] LIB.so [LIB.so ...]
+With --check-cells the host-buffer entry points are also run on a small batch for other cell
+sizes (textures, scores, filter results, refined geometry where s <= 8) and compared with the
+first library: that covers the other template instantiations a change of the shared device
+code touches.
+
+usage: python tools/variant_sweep.py [--seeds N] [--full-res] [--reps R] [--cell S]
+                                     [--check-cells 3,5,11,16] LIB.so [LIB.so ...]
 """
 import argparse
 import os
@@ -20,6 +26,8 @@ def main():
     ap.add_argument("--cell", type=int, default=7)
     ap.add_argument("--full-res", action="store_true")
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--check-cells", default="")
+    ap.add_argument("--check-seeds", type=int, default=4000)
     ap.add_argument("libs", nargs="+")
     a = ap.parse_args()
     import torch
@@ -34,6 +42,9 @@ def main():
     t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
     pos0, nrm0, ref = t(seeds["pos"]), t(seeds["nrm"]), t(seeds["ref"].astype(np.int32))
     want = None
+    check_cells = [int(x) for x in a.check_cells.split(",") if x]
+    cseeds = scenes.make_seeds(sc, a.check_seeds, seed=201)
+    cwant = {}
     for path in a.libs:
         os.environ["DENSEPOINTS_CUDA_LIB"] = os.path.abspath(path)
         capi._lib = None
@@ -73,6 +84,27 @@ def main():
         print(f"{os.path.basename(path):24s} score {best[0]:7.3f} ms {ev_score / best[0] / 1e6:6.3f} Gev/s | "
               f"filter {best[1]:7.3f} ms | refine {best[2]:8.3f} ms {ev_ref / best[2] / 1e6:6.3f} Gev/s "
               f"({ev_ref} evals) | outputs {same}", flush=True)
+        for cs in check_cells:
+          try:
+            cnv, cvi, _, _ = ctx.visibility(cseeds["pos"], cseeds["nrm"], cseeds["ref"])
+            r_ncc, r_tex, r_valid = ctx.score(cseeds["pos"], cseeds["nrm"], cseeds["ref"], cnv, cvi, cs,
+                                              want_tex=True)
+            r_keep, r_fnv, r_fvi = ctx.filter(cseeds["pos"], cseeds["nrm"], cseeds["ref"], cnv, cvi, cs)
+            res = [r_ncc, r_tex, r_valid, r_keep, r_fnv, r_fvi]
+            if cs <= 8:
+                m = r_keep.astype(bool)
+                res += list(ctx.refine(cseeds["pos"][m], cseeds["nrm"][m], cseeds["ref"][m], r_fnv[m],
+                                       r_fvi[m], cs))
+            if cs not in cwant:
+                cwant[cs] = res
+                st_ = "ref"
+            else:
+                st_ = "EQUAL" if all(np.array_equal(g, w) for g, w in zip(res, cwant[cs])) else "DIFFERS"
+            print(f"    cell {cs:2d}: {len(res)} arrays {st_}", flush=True)
+          except Exception as ex:  # keep the sweep alive: the timing lines matter most
+            import traceback
+            traceback.print_exc()
+            print(f"    cell {cs:2d}: check failed: {ex}", flush=True)
         ctx.close()
 
 
