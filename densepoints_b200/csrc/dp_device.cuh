@@ -152,6 +152,16 @@ struct __align__(16) DpViewSetup {
 };
 static_assert(sizeof(DpViewSetup) == 112, "DpViewSetup layout");
 
+// The same record without the TMA / generic-staging fields, for the group kernels (dp_group.cuh):
+// 80 bytes.  M2 and M5 are 32 x (an fp32 number), exactly representable in fp32.
+struct __align__(16) DpViewSetupG {
+  double M0, M1, M3, M4, M6, M7;
+  const uint32_t *src;
+  float M2, M5;
+  int pitch, rw, rh, ok;
+};
+static_assert(sizeof(DpViewSetupG) == 80, "DpViewSetupG layout");
+
 // ---- TMA (cp.async.bulk.tensor) staging of a patch footprint -----------------------------
 // A footprint of up to DP_TMA_BOX x DP_TMA_BOX pixels is tile-local: one elected lane issues
 // a single 2-D tensor copy of a fixed box anchored at the ROI origin (out-of-image elements
@@ -203,16 +213,49 @@ __device__ __forceinline__ void dp_mbar_wait(uint64_t *bar, unsigned parity) {
   } while (!done);
 }
 
+__device__ __forceinline__ void dp_write_setup(DpViewSetup &R, double m0, double m1, double m2,
+                                               double m3, double m4, double m5, double m6, double m7,
+                                               const uint32_t *src, int pitch, int rw, int rh, bool ok,
+                                               const void *tmap, int tlx, int tly) {
+  R.M[0] = m0; R.M[1] = m1; R.M[2] = m2; R.M[3] = m3;
+  R.M[4] = m4; R.M[5] = m5; R.M[6] = m6; R.M[7] = m7;
+  R.src = src;
+  R.pitch = pitch;
+  R.rw = rw;
+  R.rh = rh;
+  R.ok = ok ? 1 : 0;
+  const int xoff = tlx & 3;
+  const bool fits = ok && tmap != nullptr && rw + xoff <= DP_TMA_BOX && rh <= DP_TMA_BOX;
+  R.tmap = fits ? tmap : nullptr;
+  R.lgp = fits ? DP_TMA_LGP : 32 - __clz(max(rw, 1) - 1);  // ceil(log2(rw))
+  R.tlx = tlx - xoff;
+  R.tly = tly;
+  R.xoff = fits ? xoff : 0;
+}
+__device__ __forceinline__ void dp_write_setup(DpViewSetupG &R, double m0, double m1, double m2,
+                                               double m3, double m4, double m5, double m6, double m7,
+                                               const uint32_t *src, int pitch, int rw, int rh, bool ok,
+                                               const void *, int, int) {
+  R.M0 = m0; R.M1 = m1; R.M3 = m3; R.M4 = m4; R.M6 = m6; R.M7 = m7;
+  R.M2 = (float)m2;
+  R.M5 = (float)m5;
+  R.src = src;
+  R.pitch = pitch;
+  R.rw = rw;
+  R.rh = rh;
+  R.ok = ok ? 1 : 0;
+}
+
 #define DP_ROUND 16  // views whose set-up records are resident at once (per warp)
 
 // GL = lanes that share one patch (32: the whole warp; 8: four patches per warp, each group of
 // 8 lanes sets up GL/4 views of its own patch per pass and writes to its own `recs`).  kcount
 // is this group's number of views in the round, kcmax the largest kcount in the warp (the loop
 // bound must be warp-uniform: the shuffles below are full-warp).
-template <int GL = 32>
+template <int GL = 32, typename REC = DpViewSetup>
 __device__ __forceinline__ void dp_setup_views(const DpViewDev *__restrict__ views, int n_views,
                                                const int32_t *vis, int kcount, int kcmax, int s,
-                                               const DpFrame &f, DpViewSetup *recs, int lane,
+                                               const DpFrame &f, REC *recs, int lane,
                                                bool use_tma) {
   const int c = lane & 3, slot = (lane & (GL - 1)) >> 2;
   const double sgx = (c == 1 || c == 2) ? 1.0 : -1.0;  // corners (-,-) (+,-) (+,+) (-,+),
@@ -263,31 +306,17 @@ __device__ __forceinline__ void dp_setup_views(const DpViewDev *__restrict__ vie
     const double gq = (sxq * dy2 - dx2 * syq) * rden;
     const double hq = (dx1 * syq - sxq * dy1) * rden;
     if (c == 0 && active) {
-      DpViewSetup &R = recs[k];
-      R.M[0] = 32.0 * (qx1 - qx0 + gq * qx1) * inv_s;
-      R.M[1] = 32.0 * (qx3 - qx0 + hq * qx3) * inv_s;
-      R.M[2] = 32.0 * qx0;
-      R.M[3] = 32.0 * (qy1 - qy0 + gq * qy1) * inv_s;
-      R.M[4] = 32.0 * (qy3 - qy0 + hq * qy3) * inv_s;
-      R.M[5] = 32.0 * qy0;
-      R.M[6] = gq * inv_s;
-      R.M[7] = hq * inv_s;
-      const bool fin = isfinite(R.M[0]) && isfinite(R.M[1]) && isfinite(R.M[3]) &&
-                       isfinite(R.M[4]) && isfinite(R.M[6]) && isfinite(R.M[7]);
+      const double m0 = 32.0 * (qx1 - qx0 + gq * qx1) * inv_s;
+      const double m1 = 32.0 * (qx3 - qx0 + hq * qx3) * inv_s;
+      const double m3 = 32.0 * (qy1 - qy0 + gq * qy1) * inv_s;
+      const double m4 = 32.0 * (qy3 - qy0 + hq * qy3) * inv_s;
+      const double m6 = gq * inv_s, m7 = hq * inv_s;
+      const bool fin = isfinite(m0) && isfinite(m1) && isfinite(m3) && isfinite(m4) && isfinite(m6) &&
+                       isfinite(m7);
       const bool ok = all_in && rw > 0 && rh > 0 && (den != 0.0) && fin;  // optimization.cpp:45
-      R.src = V->img + (ok ? (size_t)tly * V->pitch_px + tlx : 0);
-      R.pitch = V->pitch_px;
-      R.rw = rw;
-      R.rh = rh;
-      R.ok = ok ? 1 : 0;
-      const int xoff = tlx & 3;
-      const bool fits = ok && use_tma && V->tmap != nullptr && rw + xoff <= DP_TMA_BOX &&
-                        rh <= DP_TMA_BOX;
-      R.tmap = fits ? V->tmap : nullptr;
-      R.lgp = fits ? DP_TMA_LGP : 32 - __clz(max(rw, 1) - 1);  // ceil(log2(rw))
-      R.tlx = tlx - xoff;
-      R.tly = tly;
-      R.xoff = fits ? xoff : 0;
+      dp_write_setup(recs[k], m0, m1, 32.0 * qx0, m3, m4, 32.0 * qy0, m6, m7,
+                     V->img + (ok ? (size_t)tly * V->pitch_px + tlx : 0), V->pitch_px, rw, rh, ok,
+                     use_tma ? V->tmap : nullptr, tlx, tly);
     }
   }
 }
@@ -348,8 +377,9 @@ __device__ __forceinline__ void dp_view_texture(const DpViewSetup &R, int npx, c
     double x, y;
     tx.get(j, i, x, y);
     const double Wd = fma(M6, x, fma(M7, y, 1.0));
-    double r = dp_rcp(Wd);
-    r = (Wd != 0.0) ? r : 0.0;  // W ? INTER_TAB_SIZE / W : 0
+    // W ? INTER_TAB_SIZE / W : 0 without a select: W == 0 gives r = NaN after the Newton steps,
+    // NaN coordinates, and cvt.rni.s32.f64 turns NaN into 0 like the reference's zero scale
+    const double r = dp_rcp(Wd);
     const double fX = fma(M0, x, fma(M1, y, M2)) * r;
     const double fY = fma(M3, x, fma(M4, y, M5)) * r;
     const int Xi = __double2int_rn(fX);  // saturate_cast<int>(cvRound), half to even
@@ -380,9 +410,10 @@ __device__ __forceinline__ void dp_view_texture(const DpViewSetup &R, int npx, c
     const uint32_t wx1 = (uint32_t)axw, wx0 = 32u - wx1, wy1 = (uint32_t)ayw, wy0 = 32u - wy1;
     const uint32_t br0 = (p00 & 0x00ff00ffu) * wx0 + (p01 & 0x00ff00ffu) * wx1;  // B | R<<16
     const uint32_t br1 = (p10 & 0x00ff00ffu) * wx0 + (p11 & 0x00ff00ffu) * wx1;
-    // G stays in place (bits 8..15): all its partial sums carry a factor 2^8, <= 26 bits
-    const uint32_t g0 = (p00 & 0xff00u) * wx0 + (p01 & 0xff00u) * wx1;
-    const uint32_t g1 = (p10 & 0xff00u) * wx0 + (p11 & 0xff00u) * wx1;
+    // G stays in place (bits 8..15, partial sums <= 26 bits): the blend of the whole pixel word
+    // (x byte = 0, < 2^30) minus its B | R part -- two masks less per tap pair, exact
+    const uint32_t g0 = (p00 * wx0 + p01 * wx1) - br0;
+    const uint32_t g1 = (p10 * wx0 + p11 * wx1) - br1;
     const uint32_t B = ((br0 & 0xffffu) * wy0 + (br1 & 0xffffu) * wy1 + 512u) >> 10;
     const uint32_t Rr = ((br0 >> 16) * wy0 + (br1 >> 16) * wy1 + 512u) >> 10;
     const uint32_t G = (g0 * wy0 + g1 * wy1 + (512u << 8)) >> 18;

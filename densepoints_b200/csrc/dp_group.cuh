@@ -304,7 +304,8 @@ __device__ __forceinline__ void dp_texel_fetch(const DpWarpConsts &c, const doub
   const int Xi = __double2int_rn(fX);  // saturate_cast<int>(cvRound), half to even
   const int Yi = __double2int_rn(fY);
   // BORDER_REPLICATE as a clamp of the 1/32-px coordinate (see dp_view_texture)
-  const int Xc = min(max(Xi, 0), c.xmax), Yc = min(max(Yi, 0), c.ymax);
+  // (xmax, ymax >= 0; min first, then max with 0: one VIMNMX.RELU per coordinate)
+  const int Xc = max(min(Xi, c.xmax), 0), Yc = max(min(Yi, c.ymax), 0);
   const int x0 = Xc >> 5, y0 = Yc >> 5;  // INTER_BITS = 5
   t.wx1 = (unsigned)(Xc & 31);
   t.wy1 = (unsigned)(Yc & 31);
@@ -396,13 +397,15 @@ __device__ __forceinline__ void dp_texel_loop(const DpWarpConsts &c, int npx, co
 // every tap load had at least one lane missing L1; staged, the ROI is requested once, all rows
 // at the same time, and the 4 x NP taps per lane are shared-memory reads.
 // (Measured and rejected: requesting the next view's ROI right after the texel loop of the
-// current view, so that its latency hides behind the reductions: -6 %.)
+// current view, so that its latency hides behind the reductions: -6 %; two tiles per group with
+// the next view's ROI requested a whole view ahead, cp.async groups, 56 KB of shared memory
+// per CTA: -4 %.  The staging wait is not what the warps stall on.)
 
 // Requests the ROI of one view into the group's tile; false when it does not fit the tile (the
 // taps then come straight from global memory).  The caller has made sure that the group is done
 // reading the tile.  Completion: dp_cp_async_wait_all() + __syncwarp(group).
 template <typename C>
-__device__ __forceinline__ bool dp_stage_issue(const DpViewSetup &R, uint32_t *tile,
+__device__ __forceinline__ bool dp_stage_issue(const DpViewSetupG &R, uint32_t *tile,
                                                const DpGroupLane &L) {
 #if DP_GROUP_STAGE
   constexpr int PR = C::TW / 4;    // 16-byte pieces per tile row
@@ -429,14 +432,14 @@ __device__ __forceinline__ bool dp_stage_issue(const DpViewSetup &R, uint32_t *t
 }
 
 template <typename C, bool WRITE_TEX>
-__device__ __forceinline__ void dp_view_texture_rolled(const DpViewSetup &R, int npx,
+__device__ __forceinline__ void dp_view_texture_rolled(const DpViewSetupG &R, int npx,
                                                        const double2 *txy, uint32_t *tile,
                                                        bool staged, const DpGroupLane &L,
                                                        uint8_t *gs, unsigned &ma, unsigned &mb,
                                                        uint8_t *__restrict__ tex_out) {
   DpWarpConsts c;
-  c.M0 = R.M[0]; c.M1 = R.M[1]; c.M2 = R.M[2]; c.M3 = R.M[3];
-  c.M4 = R.M[4]; c.M5 = R.M[5]; c.M6 = R.M[6]; c.M7 = R.M[7];
+  c.M0 = R.M0; c.M1 = R.M1; c.M2 = (double)R.M2; c.M3 = R.M3;
+  c.M4 = R.M4; c.M5 = (double)R.M5; c.M6 = R.M6; c.M7 = R.M7;
   c.src = R.src;
   c.pitch = R.pitch;
   c.xmax = (R.rw - 1) << 5;
@@ -465,7 +468,7 @@ template <typename C, bool WRITE_TEX, typename Sink>
 __device__ __forceinline__ void dp_eval_views_g(const DpViewDev *__restrict__ views, int n_views,
                                                 int ref, bool ref_ok, const int32_t *vis, int nv,
                                                 int s, int npx, const double n[3], const double p[3],
-                                                DpViewSetup *recs, const double2 *txy, uint8_t *gs,
+                                                DpViewSetupG *recs, const double2 *txy, uint8_t *gs,
                                                 uint32_t *tile, int lane, const DpGroupLane &L,
                                                 uint8_t *tex_base, uint8_t *valid_base, Sink sink) {
   DpFrame f;
@@ -482,14 +485,14 @@ __device__ __forceinline__ void dp_eval_views_g(const DpViewDev *__restrict__ vi
     const int kc = min(max(nv - k0, 0), GROUND);   // this group's views in the round
     const int kcmax = min(GROUND, nvmax - k0);     // warp-uniform loop bound
     __syncwarp();
-    dp_setup_views<GL>(views, n_views, vis + k0, kc, kcmax, s, f, recs, lane, false);
+    dp_setup_views<GL, DpViewSetupG>(views, n_views, vis + k0, kc, kcmax, s, f, recs, lane, false);
     __syncwarp();
     unsigned my1 = 0, my2 = 0;
     double mynum = 0.0;
     int myok = 0;
 #pragma unroll 1
     for (int l = 0; l < kcmax; ++l) {
-      const DpViewSetup &R = recs[l];
+      const DpViewSetupG &R = recs[l];
       const bool ok = l < kc && R.ok != 0;  // uniform inside the group
       unsigned s1 = 0, s2 = 0;
       double num = 0.0;
@@ -546,7 +549,7 @@ template <typename C>
 __device__ __forceinline__ double dp_objective_g(const DpViewDev *__restrict__ views, int n_views,
                                                  int ref, const int32_t *vis, int nv, int s, int npx,
                                                  const double n[3], const double p[3],
-                                                 DpViewSetup *recs, const double2 *txy,
+                                                 DpViewSetupG *recs, const double2 *txy,
                                                  uint8_t *gs, uint32_t *tile, int lane,
                                                  const DpGroupLane &L) {
   double sum = 0.0;
@@ -566,7 +569,7 @@ __device__ __forceinline__ double dp_objective_g(const DpViewDev *__restrict__ v
 // Shared memory of a CTA of the group kernels.
 template <typename C>
 struct DpGroupShared {
-  DpViewSetup recs[DP_GWARPS][C::GROUPS][C::GROUND];
+  DpViewSetupG recs[DP_GWARPS][C::GROUPS][C::GROUND];
   double2 txy[C::NP * C::GL];
   // +32 words: the neighbour taps of an edge pixel (weight 0) may read past the last tile
   __align__(16) uint32_t tile[DP_GROUP_STAGE ? DP_GWARPS * C::GROUPS * C::TSTRIDE + 32 : 4];
@@ -666,7 +669,7 @@ __global__ void __launch_bounds__(DP_GWARPS * 32, DP_GMINCTA) dp_refine_group_ke
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const DpGroupLane L = dp_group_lane<GL>(lane);
   const int grp = lane / GL;
-  DpViewSetup *recs = sh.recs[warp][grp];
+  DpViewSetupG *recs = sh.recs[warp][grp];
   DpNelderMead &S = nm_s[warp][grp];
   if (L.leader) {  // defined values for the lockstep evaluations of a group without a patch
     double *z = reinterpret_cast<double *>(&S);

@@ -46,6 +46,9 @@ def main():
     cseeds = scenes.make_seeds(sc, a.check_seeds, seed=201)
     cwant = {}
     for path in a.libs:
+        if not os.path.exists(path):
+            print(f"{os.path.basename(path):24s} missing, skipped", flush=True)
+            continue
         os.environ["DENSEPOINTS_CUDA_LIB"] = os.path.abspath(path)
         capi._lib = None
         ctx = capi.Context(0)
