@@ -97,10 +97,17 @@ class ClockSampler(threading.Thread):
 
 def make_workload(n_seeds, rank=0, small=False):
     from densepoints_b200 import scenes
-    if small:
-        sc = scenes.make_sphere_scene(seed=2, n_views=16, width=640, height=480, f=500.0)
-    else:
-        sc = scenes.make_sphere_scene(seed=2, n_views=16, width=1280, height=960, f=1000.0)
+    cache = os.environ.get("DP_SCENE_CACHE")      # profiling runs: render the scene once per box
+    w, h, f = (640, 480, 500.0) if small else (1280, 960, 1000.0)
+    sc = None
+    if cache and os.path.exists(f"{cache}.{w}.npz"):
+        z = np.load(f"{cache}.{w}.npz")
+        sc = scenes.Scene("C2-sphere", z["P"], list(z["images"]), w, h, "sphere", radius=5.0,
+                          centers=z["centers"])
+    if sc is None:
+        sc = scenes.make_sphere_scene(seed=2, n_views=16, width=w, height=h, f=f)
+        if cache and rank == 0:
+            np.savez(f"{cache}.{w}.npz", P=sc.P, images=np.stack(sc.images), centers=sc.centers)
     seeds = scenes.make_seeds(sc, n_seeds, seed=200 + rank)
     return sc, seeds
 
