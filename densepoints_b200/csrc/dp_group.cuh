@@ -399,7 +399,8 @@ __device__ __forceinline__ void dp_texel_loop(const DpWarpConsts &c, int npx, co
 // (Measured and rejected: requesting the next view's ROI right after the texel loop of the
 // current view, so that its latency hides behind the reductions: -6 %; two tiles per group with
 // the next view's ROI requested a whole view ahead, cp.async groups, 56 KB of shared memory
-// per CTA: -4 %.  The staging wait is not what the warps stall on.)
+// per CTA: -4 %.  The staging wait is not what the warps stall on.  The rarely used unstaged
+// texel loop out of line, to make the hot path's code smaller: -2 %.)
 
 // Requests the ROI of one view into the group's tile; false when it does not fit the tile (the
 // taps then come straight from global memory).  The caller has made sure that the group is done
