@@ -1,4 +1,4 @@
-"""N>1 host logic on CPU: two gloo ranks run the multi-GPU expansion driver
+"""N>1 host logic on CPU: two and three gloo ranks (even and ragged view ownership) run the multi-GPU expansion driver
 (densepoints_b200/distributed.py) over an oracle-backed level backend; both must end with
 the store and grids of the single-process 1-thread FIFO."""
 import os
@@ -71,7 +71,7 @@ def _worker(rank, world, port, outdir):
     from oracle import oracle as orc
     # every rank renders its slice of the views, then the images are exchanged
     sc, seeds = _scene(only_views=dd.views_of_rank(4, rank, world))
-    assert not sc.images[(rank + 1) % world].any()
+    assert not sc.images[(rank + 1) % world].any()       # a view this rank did not render
     dd.share_images(sc.images, rank, world)
     full, _ = _scene()
     assert all(np.array_equal(a, b) for a, b in zip(sc.images, full.images))
@@ -97,7 +97,11 @@ def test_partition_views_is_contiguous_and_balanced():
     assert (dd.partition_views(ref, 8, 1) == 0).all()
 
 
-def test_two_rank_expansion_matches_single_process_fifo(orc):
+import pytest
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_multi_rank_expansion_matches_single_process_fifo(orc, world):
     sc, seeds = _scene()
     V = orc.Views(sc.P, sc.images)
     prm = orc.default_params(minimum_visible_image=2)
@@ -110,12 +114,14 @@ def test_two_rank_expansion_matches_single_process_fifo(orc):
     assert ref_org.size() > n_seed
     with tempfile.TemporaryDirectory() as d:
         port = 29500 + (os.getpid() % 2000)
-        mp.spawn(_worker, args=(2, port, d), nprocs=2, join=True)
-        got = [dict(np.load(os.path.join(d, f"rank{r}.npz"))) for r in range(2)]
+        mp.spawn(_worker, args=(world, port + world, d), nprocs=world, join=True)
+        got = [dict(np.load(os.path.join(d, f"rank{r}.npz"))) for r in range(world)]
     grids = np.concatenate([ref_org.grid(v).ravel() for v in range(sc.n_views)])
     for g in got:
         for k in want:
             assert np.array_equal(g[k], want[k]), k
         assert np.array_equal(g["grids"], grids)
-    # the work really was split: both ranks produced records, none produced all of them
-    assert all(0 < int(g["local"]) < int(g["passed"]) for g in got)
+    # the work really was split: no rank produced all the records, together they produced all
+    assert all(int(g["local"]) < int(g["passed"]) for g in got)
+    assert sum(int(g["local"]) for g in got) == int(got[0]["passed"])
+    assert sum(int(g["local"]) > 0 for g in got) >= 2
