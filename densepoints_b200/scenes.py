@@ -120,8 +120,50 @@ def _render(P_list, centers, Rs, f, cx, cy, width, height, surface, param, tex, 
     return images
 
 
+def _render_torch(centers, Rs, f, cx, cy, width, height, surface, param, tex, device):
+    """_render on a torch device (fp64): for the large benchmark scenes only (64 x 1920x1080 takes
+    minutes in numpy).  Test-data plumbing, not the product; pixel values may differ from the
+    numpy renderer in the last bit of sin(), so golden vectors always use _render."""
+    import torch
+    dev = torch.device(device)
+    t64 = lambda a: torch.as_tensor(np.asarray(a, np.float64), device=dev)
+    jj, ii = torch.meshgrid(torch.arange(width, dtype=torch.float64, device=dev),
+                            torch.arange(height, dtype=torch.float64, device=dev), indexing="xy")
+    pix = torch.stack([(jj.reshape(-1) - cx) / f, (ii.reshape(-1) - cy) / f,
+                       torch.ones(width * height, dtype=torch.float64, device=dev)], 1)
+    kb, pb = t64(tex.kb), t64(tex.pb)
+    kc = [(t64(k), t64(p)) for k, p in tex.kc]
+    images = []
+    for C0, R in zip(centers, Rs):
+        C0t, Rt = t64(C0), t64(R)
+        d = pix @ Rt
+        if surface == "plane":
+            t = -C0t[2] / d[:, 2]
+            hit = t > 0
+        else:
+            b = d @ C0t
+            a = (d * d).sum(1)
+            disc = b * b - a * (C0t @ C0t - param * param)
+            hit = disc > 0
+            t = (-b - torch.sqrt(torch.where(hit, disc, torch.zeros_like(disc)))) / a
+            hit &= t > 0
+        X = C0t[None, :] + t[:, None] * d
+        base = torch.sin(X @ kb.T + pb).sum(1) / np.sqrt(tex.n_base / 2.0)
+        col = torch.empty((X.shape[0], 3), dtype=torch.uint8, device=dev)
+        for c in range(3):
+            ch = torch.sin(X @ kc[c][0].T + kc[c][1]).sum(1) / np.sqrt(tex.n_chan / 2.0)
+            v = 128.0 + 48.0 * base + 24.0 * ch
+            col[:, c] = torch.clamp(torch.round(v), 0, 255).to(torch.uint8)
+        if surface == "plane":
+            hit &= (X[:, 0].abs() <= param) & (X[:, 1].abs() <= param)
+        col = torch.where(hit[:, None], col, torch.full_like(col, 37))
+        images.append(col.reshape(height, width, 3).cpu().numpy())
+    return images
+
+
 def make_plane_scene(seed=1, n_views=3, width=640, height=480, f=None, distance=20.0,
-                     yaw_spread_deg=15.0, extent=None, name="C1-plane", only_views=None):
+                     yaw_spread_deg=15.0, extent=None, name="C1-plane", only_views=None,
+                     device=None):
     """Config C1: textured plane z=0 seen by `n_views` TestScene-style pinholes
     (test_data_generator.cpp:8-13 scaled to the image: f = width/4 * ... ) placed on an
     arc at `distance` with +-yaw_spread around the plane normal."""
@@ -141,8 +183,11 @@ def make_plane_scene(seed=1, n_views=3, width=640, height=480, f=None, distance=
         Ps.append(projection(f, cx, cy, R, c))
     px_world = distance / f
     tex = Texture3D(seed + 1000, (3.0 * px_world, 14.0 * px_world))
-    images = _render(Ps, centers, Rs, f, cx, cy, width, height, "plane", extent, tex,
-                     only_views=only_views)
+    if device is not None and only_views is None:
+        images = _render_torch(centers, Rs, f, cx, cy, width, height, "plane", extent, tex, device)
+    else:
+        images = _render(Ps, centers, Rs, f, cx, cy, width, height, "plane", extent, tex,
+                         only_views=only_views)
     return Scene(name, np.array(Ps), images, width, height, "plane", extent=extent,
                  centers=np.array(centers))
 
@@ -206,8 +251,10 @@ def make_seeds(scene: Scene, n, seed=0, depth_noise=0.01, tilt_deg=10.0):
             X = np.vstack([X, d * scene.radius])
         X = X[:n]
         nin = -X / scene.radius
-    dist = np.linalg.norm(X[:, None, :] - C[None, :, :], axis=2)
-    ref = np.argmin(dist, axis=1).astype(np.int32)
+    ref = np.empty(n, np.int32)
+    for s0 in range(0, n, 1 << 18):       # chunked: n x views x 3 doubles at once is GBs for 1e6+
+        dist = np.linalg.norm(X[s0:s0 + (1 << 18), None, :] - C[None, :, :], axis=2)
+        ref[s0:s0 + (1 << 18)] = np.argmin(dist, axis=1)
     Cr = C[ref]
     depth = rng.uniform(-depth_noise, depth_noise, n)[:, None]
     pos = Cr + (1.0 + depth) * (X - Cr)
