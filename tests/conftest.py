@@ -34,6 +34,11 @@ def golden_primitives():
 
 
 @pytest.fixture(scope="session")
+def golden_primitives_wide():
+    return dict(np.load(os.path.join(GOLDEN, "golden_primitives_wide.npz")))
+
+
+@pytest.fixture(scope="session")
 def golden_views(orc, golden_scoring):
     g = golden_scoring
     return orc.Views(g["P"], list(g["images"]))

@@ -42,6 +42,25 @@ def test_golden_homography_and_warp(orc, golden_primitives):
         assert np.array_equal(orc.warp_perspective(sub, H, s), tex[:s, :s])        # cv2's H
 
 
+def test_golden_homography_and_warp_wide(orc, golden_primitives_wide):
+    """cv2 vectors for the cell sizes / ROI shapes the first set does not hold: s in
+    {2,3,4,6,8,9,13,20,32}, ROIs up to 48 px, keystone quads, quads mostly outside their ROI
+    (BORDER_REPLICATE on most texels), 1-pixel ROIs (tests/golden/make_golden_wide.py)."""
+    g = golden_primitives_wide
+    img = g["image"]
+    assert set(int(k) for k in g["kind"]) == {0, 1, 2, 3} and len(g["s"]) >= 300
+    for quad, s, roi, H, tex in zip(g["quad"], g["s"], g["roi"], g["H"], g["tex"]):
+        s = int(s)
+        cell = np.array([[0, 0], [s, 0], [s, s], [0, s]], np.float32)
+        Ho = orc.find_homography4(quad, cell)
+        assert Ho is not None
+        assert np.abs(Ho - H).max() <= 1e-9 * max(1.0, np.abs(H).max())
+        x0, y0, w, h = (int(v) for v in roi)
+        sub = img[y0:y0 + h, x0:x0 + w]
+        assert np.array_equal(orc.warp_perspective(sub, Ho, s), tex[:s, :s])
+        assert np.array_equal(orc.warp_perspective(sub, H, s), tex[:s, :s])
+
+
 def test_golden_gray(orc, golden_primitives):
     g = golden_primitives
     mine = np.array([orc.gray(*px) for px in g["gray_px"]])
