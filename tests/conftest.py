@@ -34,6 +34,11 @@ def golden_primitives():
 
 
 @pytest.fixture(scope="session")
+def golden_scoring_sphere():
+    return dict(np.load(os.path.join(GOLDEN, "golden_scoring_sphere.npz")))
+
+
+@pytest.fixture(scope="session")
 def golden_primitives_wide():
     return dict(np.load(os.path.join(GOLDEN, "golden_primitives_wide.npz")))
 

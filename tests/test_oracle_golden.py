@@ -93,3 +93,26 @@ def test_golden_textures_ncc_filter(orc, golden_scoring, golden_views):
     for v in range(golden_views.n):
         assert np.abs(golden_views.center(v) - g["center"][v]).max() < 1e-9
         assert np.abs(golden_views.xaxis(v) - g["xaxis"][v]).max() < 1e-12
+
+
+def test_golden_sphere_textures_ncc_filter(orc, golden_scoring_sphere):
+    """The same chain against cv2 on a curved scene (sphere, 6 views, patches tilted up to 30
+    degrees, default minimum_visible_image = 3) at s = 3, 8, 13, 20
+    (tests/golden/make_golden_sphere.py); at s = 3 most ROIs shrink to nothing (empty textures)."""
+    g = golden_scoring_sphere
+    V = orc.Views(g["P"], list(g["images"]))
+    for s in (3, 8, 13, 20):
+        ncc, tex, valid = orc.score_batch(V, g["pos"], g["nrm"], g["ref"], g["nvis"], g["vis"], s,
+                                          want_tex=True)
+        assert np.array_equal(valid, g[f"valid{s}"])
+        m = g[f"valid{s}"].astype(bool)
+        assert np.array_equal(tex[m], g[f"tex{s}"][m])
+        k = np.arange(g["vis"].shape[1])[None, :]
+        sm = (k >= 1) & (k < g["nvis"][:, None])
+        assert np.abs(ncc[sm] - g[f"ncc{s}"][sm]).max() < 2e-6
+        keep, fnvis, fvis = orc.filter_batch(V, g["pos"], g["nrm"], g["ref"], g["nvis"], g["vis"],
+                                             s, 0.6, 3)
+        assert np.array_equal(keep, g[f"keep{s}"])
+        assert np.array_equal(fnvis, g[f"fnvis{s}"])
+        assert np.array_equal(fvis, g[f"fvis{s}"])
+    assert g["valid3"].sum() < 0.75 * g["valid8"].sum()      # the empty-texture path is exercised
