@@ -7,6 +7,11 @@ pytestmark = pytest.mark.gpu
 
 
 def test_golden_sphere_textures_ncc_filter(golden_scoring_sphere):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from densepoints_b200 import build as b
+    b.build_cuda()
     from densepoints_b200 import capi
     g = golden_scoring_sphere
     ctx = capi.Context(0)                      # minimum_visible_image = 3, threshold 0.6
