@@ -11,12 +11,12 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _build_driver(tmp):
+def _build_driver(tmp, name="host_mirror_test"):
     from densepoints_b200 import build as b
     lib = b.build_cuda()
-    exe = os.path.join(tmp, "host_mirror_test")
+    exe = os.path.join(tmp, name)
     cmd = ["/usr/bin/g++", "-std=c++14", "-O2", "-Wall", "-I" + os.path.join(ROOT, "densepoints_b200", "host"),
-           "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "host_mirror_test.cpp"),
+           "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", name + ".cpp"),
            "-o", exe, "-L" + os.path.dirname(lib), "-ldensepoints_cuda",
            "-Wl,-rpath," + os.path.dirname(lib)]
     env = dict(os.environ)
@@ -29,6 +29,14 @@ def _build_driver(tmp):
 def test_host_mirror_compiles(tmp_path):
     """CPU: the mirror headers + driver compile and link against the C ABI."""
     assert os.path.exists(_build_driver(str(tmp_path)))
+
+
+def test_pmvs_facade_compiles(tmp_path):
+    """CPU: the mirrored method facade (PMVS::AddCamera / Run / GetPointCloud, reference
+    pmvs.h:14-35) driven like programs/densify compiles, links and starts."""
+    exe = _build_driver(str(tmp_path), "pmvs_facade_check")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "usage" in r.stdout
 
 
 def _read_patches(f, n_views):
