@@ -11,10 +11,20 @@ Workload (N=1): BASELINE.json configs[1] -- synthetic textured sphere, 16 views
 1M-seed shard of the same scene (weak scaling, no data-path collective).
 
   value  = patch-view evals/s with the seeds resident in HBM (dp_*_dev entry points)
-  e2e    = the same through the host-buffer C ABI (dp_filter + dp_refine on pinned host
-           arrays, H2D/D2H inside the timed region)
-  roofline = the refine kernel (dp_refine_group_kernel) against the measured HBM copy bandwidth
+  e2e    = the same through the host-buffer C ABI (dp_filter_refine on pinned host arrays,
+           H2D/D2H inside the timed region)
+  roofline = the refine kernel against the measured HBM copy bandwidth (+ the issue roof)
   cpu_baseline = the CPU oracle (OpenMP, all host threads) on a bounded sample
+
+Two more legs ride on the same line (both at every N):
+  expansion    BASELINE configs[3] style -- 64 views 1920x1080, 50 000 seeds (mu = 16 filter +
+               refine), Expand::ExpandPatches at mu = 11 -- with the patches sharded by reference
+               image over the N ranks and one NCCL allgather per BFS level (STRONG scaling: the
+               scene is fixed).  Reports refined patches/s, per-level local / allgather / commit
+               times (max over ranks) and a sha256 of the final store + occupancy grids, which
+               must be identical on every rank and for every N.
+  roofline_hbm the score / refine kernels on that scene, whose 531 MB image set does not fit
+               L2: the regime the HBM peak actually bounds.
 
 `--impl reference` times the CPU oracle alone (the reference C++ cannot be built here:
 no OpenCV/Eigen/PCL headers).
@@ -42,14 +52,18 @@ def b_alg(s, nv):
     return 3.0 * (2 * (s // 2) + 2) ** 2 + 4.0 + (28.0 + 2.0 * nv) / max(nv, 1)
 
 
-def ncu_refine_capture():
-    """dram bytes / instruction counts of the refine kernel on this workload, from the committed
-    ncu --set full capture (profiles/r01_refine_traffic.json); None if absent."""
-    p = os.path.join(ROOT, "profiles", "r01_refine_traffic.json")
+def ncu_capture(name):
+    """(capture, stale): DRAM bytes / instruction counts of a kernel on this workload from a
+    committed `ncu --set full` extract (profiles/<name>, written by tools/ncu_extract.py together
+    with a hash of the CUDA sources it profiled).  stale = the library built now is not the one
+    that was profiled: the caller then reports traffic / issue as null."""
+    p = os.path.join(ROOT, "profiles", name)
     try:
-        return json.load(open(p))
+        cap = json.load(open(p))
     except Exception:
-        return None
+        return None, False
+    from densepoints_b200 import build as dpbuild
+    return cap, cap.get("src_sha256") != dpbuild.source_hash()
 
 
 def hbm_peak():
@@ -166,6 +180,175 @@ def workload_name(args):
             f"{args.seeds} seed patches per GPU, Seed::FilterPatches + OptimizePatches, mu=7")
 
 
+EXP_VIEWS, EXP_W, EXP_H, EXP_SEEDS, EXP_SEED_CELL, EXP_CELL, EXP_MAX_LEVELS = 64, 1920, 1080, 50_000, 16, 11, 12
+
+
+def store_digest(ctx):
+    """sha256 over the organizer's patch store (pos, nrm, rgb, ref, nvis, vis) and all
+    occupancy grids."""
+    import hashlib
+    ex = ctx.organizer_export()
+    h = hashlib.sha256()
+    for k in ("pos", "nrm", "rgb", "ref", "nvis", "vis"):
+        h.update(np.ascontiguousarray(ex[k]).tobytes())
+    h.update(ctx.organizer_grids().tobytes())
+    return h.hexdigest(), len(ex["ref"])
+
+
+def run_expansion_and_hbm(args, rank, world, local_rank, dev):
+    """The sharded expansion (reference expand.cpp:34-143 / patch_organizer.cpp:42-65)
+    and the HBM-bound scoring regime, both on one 64-view 1920x1080 scene."""
+    import torch
+    import torch.distributed as dist
+    from densepoints_b200 import capi, scenes
+    from densepoints_b200 import distributed as dd
+    small = args.small
+    nv_, w_, h_ = (16, 640, 360) if small else (EXP_VIEWS, EXP_W, EXP_H)
+    n_seeds = 4000 if small else EXP_SEEDS
+    t0 = time.perf_counter()
+    sc = scenes.make_plane_scene(seed=4, n_views=nv_, width=w_, height=h_, yaw_spread_deg=25.0,
+                                 name="C4", device=f"cuda:{local_rank}",
+                                 only_views=dd.views_of_rank(nv_, rank, world) if world > 1 else None)
+    dd.share_images(sc.images, rank, world, dev)       # views are replicated (SURVEY 8e)
+    scene_s = time.perf_counter() - t0
+    seeds = scenes.make_seeds(sc, n_seeds, seed=40, depth_noise=0.003, tilt_deg=5.0)
+    ctx = capi.Context(local_rank)
+    t0 = time.perf_counter()
+    ctx.set_views(sc.P, sc.images)
+    upload_s = time.perf_counter() - t0
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # seed stage (replicated on every rank; not part of the sharded-expansion timing)
+    sync()
+    t0 = time.perf_counter()
+    nvis, vis, _, _ = ctx.visibility(seeds["pos"], seeds["nrm"], seeds["ref"])
+    keep, fnvis, fvis, pos, nrm, evs = ctx.filter_refine(seeds["pos"], seeds["nrm"], seeds["ref"],
+                                                        nvis, vis, EXP_SEED_CELL)
+    m = keep.astype(bool)
+    seed_s = time.perf_counter() - t0
+    be = dd.CudaLevelBackend(ctx, dev)
+
+    def one_run():
+        ctx.organizer_reset()
+        acc = ctx.organizer_insert(pos[m], nrm[m], seeds["ref"][m], fnvis[m], fvis[m])
+        tm = {}
+        sync()
+        t1 = time.perf_counter()
+        st = dd.expand_distributed(be, EXP_CELL, EXP_MAX_LEVELS, rank, world, None, timings=tm)
+        sync()
+        return st, tm, time.perf_counter() - t1, int(acc.sum())
+
+    one_run()                                            # warm-up (allocations, NCCL channels)
+    st, tm, wall_s, seeded = one_run()
+    digest, n_store = store_digest(ctx)
+    # max over ranks of the per-level phase times; sum over ranks of the candidates refined
+    L = st["levels"]
+    tv = torch.tensor([tm["local_ms"], tm["allgather_ms"], tm["commit_ms"]], dtype=torch.float64,
+                      device=dev).reshape(3, L)
+    tmin = tv[0].clone()
+    cand = torch.tensor(tm["local_candidates"], dtype=torch.float64, device=dev)
+    wall = torch.tensor([wall_s], dtype=torch.float64, device=dev)
+    ok = torch.ones(1, dtype=torch.int32, device=dev)
+    if world > 1:
+        dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        dist.all_reduce(cand, op=dist.ReduceOp.SUM)
+        dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+        hs = [None] * world
+        dist.all_gather_object(hs, digest)
+        ok[0] = 1 if all(h == hs[0] for h in hs) else 0
+    level_ms = (tv[0] + tv[1] + tv[2]).tolist()
+    total_ms = float(sum(level_ms))
+    cand_total = float(cand.sum().item())
+    exp = {"workload": f"BASELINE configs[3] style: {nv_} views {w_}x{h_} plane scene, {n_seeds} seeds "
+                       f"(mu={EXP_SEED_CELL} filter + refine), Expand::ExpandPatches at mu={EXP_CELL}, "
+                       f"level cap {EXP_MAX_LEVELS}",
+           "scaling": "strong", "n_gpus": world,
+           "sharding": "patches by reference image (ownership re-balanced per level by the "
+                       "frontier's work per view), one NCCL allgather of candidate records per level",
+           "levels": L, "seeds_kept": int(m.sum()), "seeds_inserted": seeded,
+           "patches": n_store, "candidates_refined": int(cand_total), "records_gathered": st["passed"],
+           "inserted": st["inserted"], "record_bytes": ctx.record_bytes(),
+           "refined_patches_per_s": cand_total / (total_ms * 1e-3) if total_ms > 0 else None,
+           "expansion_ms": total_ms, "wall_ms": float(wall.item()) * 1e3,
+           "level_ms": level_ms, "local_ms": tv[0].tolist(), "local_ms_min_rank": tmin.tolist(),
+           "allgather_ms": tv[1].tolist(), "commit_ms": tv[2].tolist(),
+           "frontier": tm["frontier"], "records_per_level": tm["records"],
+           "seed_stage_ms_replicated": seed_s * 1e3, "scene_render_s": scene_s,
+           "view_upload_s": upload_s, "store_sha256": digest, "ranks_equal": bool(ok.item())}
+
+    # ---- HBM-bound regime: the same scene (image set >> L2), many patches, mu = 7 -----------
+    hbm = None
+    try:
+        n = 200_000 if small else 1_500_000
+        sd = scenes.make_seeds(sc, n, seed=41 + rank, depth_noise=0.003, tilt_deg=5.0)
+        V = sc.n_views
+        stream = torch.cuda.current_stream().cuda_stream
+        t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+        p0, n0, rf = t(sd["pos"]), t(sd["nrm"]), t(sd["ref"].astype(np.int32))
+        nvis0 = torch.zeros(n, dtype=torch.int32, device=dev)
+        vis0 = torch.full((n, V), -1, dtype=torch.int32, device=dev)
+        ctx.visibility_dev(capi.dev_batch(n, V, p0.data_ptr(), n0.data_ptr(), rf.data_ptr(),
+                                          nvis0.data_ptr(), vis0.data_ptr()), stream=stream)
+        p1, n1, nv1, vi1 = (torch.empty_like(x) for x in (p0, n0, nvis0, vis0))
+        ncc = torch.zeros((n, V), dtype=torch.float32, device=dev)
+        kp = torch.zeros(n, dtype=torch.uint8, device=dev)
+        evl = torch.zeros(n, dtype=torch.int32, device=dev)
+        wb = capi.dev_batch(n, V, p1.data_ptr(), n1.data_ptr(), rf.data_ptr(), nv1.data_ptr(),
+                            vi1.data_ptr())
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        best = [1e30] * 3
+        for rep in range(3):
+            flush.zero_()
+            p1.copy_(p0); n1.copy_(n0); nv1.copy_(nvis0); vi1.copy_(vis0)
+            e[0].record()
+            ctx.score_dev(wb, CELL, ncc.data_ptr(), stream=stream)
+            e[1].record()
+            ctx.filter_dev(wb, CELL, kp.data_ptr(), stream=stream)
+            e[2].record()
+            ctx.refine_dev(wb, CELL, mask_ptr=kp.data_ptr(), evals_ptr=evl.data_ptr(), stream=stream)
+            e[3].record()
+            torch.cuda.synchronize()
+            best = [min(b, e[i].elapsed_time(e[i + 1])) for i, b in enumerate(best)]
+        ev_score = int(nvis0.sum().item())
+        ev_ref = int((evl.long() * nv1.long() * kp.long()).sum().item())
+        mean_nv = ev_score / max(n, 1)
+        mean_nv_ref = float((nv1.double() * kp).sum().item() / max(int(kp.sum().item()), 1))
+        peak, peak_src = hbm_peak()
+        gbs = lambda ev, ms, nvv: ev * b_alg(CELL, nvv) / (ms * 1e-3) / 1e9
+        cap, stale = ncu_capture("r02_hbm_traffic.json")
+        if args.small:
+            cap = None
+        tr = (cap or {}).get("score_dram_bytes_per_launch") if not stale else None
+        hbm = {"workload": f"{V} views {w_}x{h_} BGRx image set = "
+                           f"{V * h_ * ((w_ + 31) // 32 * 32) * 4 / 1e6:.0f} MB (> 126 MB L2), "
+                           f"{n} patches per GPU in random order, mu={CELL}",
+               "kernel": "dp_score_group_kernel (all visible views of every patch)",
+               "bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src,
+               "mean_visible_views": mean_nv, "alg_bytes_per_eval": b_alg(CELL, mean_nv),
+               "achieved": gbs(ev_score, best[0], mean_nv), "frac": gbs(ev_score, best[0], mean_nv) / peak,
+               "score_ms": best[0], "score_evals_per_s": ev_score / best[0] * 1e3,
+               "traffic": tr,
+               "traffic_over_algorithmic": (tr / (ev_score * b_alg(CELL, mean_nv))) if tr else None,
+               "stale_profile": bool(stale) if cap else None,
+               "refine": {"ms": best[2], "evals_per_s": ev_ref / best[2] * 1e3,
+                          "achieved": gbs(ev_ref, best[2], mean_nv_ref),
+                          "frac": gbs(ev_ref, best[2], mean_nv_ref) / peak,
+                          "traffic": (cap or {}).get("refine_dram_bytes_per_launch") if not stale else None},
+               "filter_ms": best[1]}
+        del p0, n0, rf, nvis0, vis0, p1, n1, nv1, vi1, ncc, kp, evl, flush
+    except Exception as ex:          # the extra leg must never take the bench line down
+        hbm = {"error": repr(ex)}
+    launches = ctx.launch_count()
+    ctx.close()
+    return exp, hbm, launches
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -176,6 +359,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=16384)
     ap.add_argument("--small", action="store_true", help="reduced scene/seed count (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-legs", action="store_true",
+                    help="skip the expansion / HBM-regime legs (profiling runs)")
     args = ap.parse_args()
     if args.small and args.seeds == 1 << 20:
         args.seeds = 1 << 15
@@ -292,7 +477,7 @@ def main():
 
     # one pristine pinned copy of the caller's arrays per e2e step (dp_filter_refine edits its
     # arguments in place, like the reference edits its std::vector<Patch>)
-    e2e_steps = max(1, min(args.steps, 2))
+    e2e_steps = max(1, min(args.steps, 10))
     work = []
     for _ in range(e2e_steps + 1):
         work.append([pinned(x.copy()) for x in (h_pos, h_nrm, h_nvis, h_vis)])
@@ -326,6 +511,10 @@ def main():
         dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
         dist.all_reduce(e2e_ev, op=dist.ReduceOp.SUM)
     e2e_value = float(e2e_ev.item()) / float(e2e_dt.item())
+    e2e_ref = torch.tensor([float(k_h.astype(bool).sum()) * e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ref, op=dist.ReduceOp.SUM)
+    e2e_refined_per_s = float(e2e_ref.item()) / float(e2e_dt.item())
     n_keep = int(keep.sum().item())
     h2d = n * (12 + 12 + 4 + 4 + 4 * V)
     d2h = n * (1 + 4 + 4 * V + 12 + 12 + 4)
@@ -336,10 +525,14 @@ def main():
     alg_bytes = e_refine * b_alg(CELL, mean_nv)
     peak, peak_src = hbm_peak()
     achieved = alg_bytes / (refine_kernel_ms * 1e-3) / 1e9
-    cap = ncu_refine_capture() if not args.small and args.seeds == 1 << 20 else None
+    cap, stale = ncu_capture("r02_refine_traffic.json")
+    if args.small or args.seeds != 1 << 20:
+        cap = None
+    live = cap if (cap and not stale) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak,
-                "traffic": cap["dram_bytes_per_launch"] if cap else None,
+                "traffic": live["dram_bytes_per_launch"] if live else None,
+                "stale_profile": bool(stale) if cap else None,
                 "kernel": cap["kernel"] if cap else "dp_refine_group_kernel<DpGroupCfg<4, 13, 16, 8>>",
                 "kernel_ms": refine_kernel_ms, "peak_source": peak_src,
                 "alg_bytes_per_eval": b_alg(CELL, mean_nv), "alg_bytes_per_launch": alg_bytes,
@@ -348,7 +541,9 @@ def main():
                         "HBM: the 79 MB BGRx image set is L2-resident and DRAM traffic is <1% of "
                         "the algorithmic bytes; see roofline.issue for warp instructions per "
                         "patch-view eval and the issue-slot fraction (ncu)"}
-    if cap:
+    roofline["issue"] = None
+    if live:
+        cap = live
         sm = 148
         issue_peak = sm * 4 * (clocks["sm_mhz"] or 1965.0) * 1e6       # warp-inst/s
         inst_per_eval = cap["warp_inst_per_launch"] / cap["evals_per_launch"]
@@ -382,6 +577,14 @@ def main():
                          f"(OpenMP); {dt:.1f} s",
                "refined_patches_per_s": float(m.sum()) / dt}
 
+    launches_main = launches
+    ctx.close()
+    del pos0, nrm0, ref, nvis0, vis0, pos, nrm, nvis, vis, keep, evals, flush
+    torch.cuda.empty_cache()
+    expansion = hbm_leg = None
+    if not args.no_extra_legs:
+        expansion, hbm_leg, _ = run_expansion_and_hbm(args, rank, world, local_rank, dev)
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": max_ms / args.steps,
@@ -395,11 +598,11 @@ def main():
                            "l2": "256 MB buffer written between iterations (L2 flush), inside the "
                                  "timed region"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": d2h, "steps": e2e_steps},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-                "cpu_baseline": cpu}
+                        "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                        "refined_patches_per_s": e2e_refined_per_s},
+                "gpu_launches": launches_main, "clocks": clocks, "roofline": roofline,
+                "cpu_baseline": cpu, "expansion": expansion, "roofline_hbm": hbm_leg}
         print(json.dumps(line), flush=True)
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
 

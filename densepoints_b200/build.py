@@ -30,6 +30,17 @@ def sources():
                   [os.path.join(root, "include", "densepoints_cuda.h")])
 
 
+def source_hash() -> str:
+    """sha256 over the CUDA sources and the C ABI header: ties a committed ncu extract
+    (profiles/*.json, written by tools/ncu_extract.py) to the code it profiled."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sources():
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()
+
+
 def build_cuda(force: bool = False, verbose: bool = False) -> str:
     srcs = sources()
     stale = (not os.path.exists(LIB)) or any(os.path.getmtime(s) > os.path.getmtime(LIB)

@@ -63,6 +63,8 @@ def lib():
         L.dp_launch_count.argtypes = [C.c_void_p]
         L.dp_organizer_size.restype = C.c_int64
         L.dp_organizer_size.argtypes = [C.c_void_p]
+        L.dp_expand_last_candidates.restype = C.c_int64
+        L.dp_expand_last_candidates.argtypes = [C.c_void_p]
         L.dp_record_bytes.restype = C.c_size_t
         L.dp_record_bytes.argtypes = [C.c_void_p]
         L.dp_destroy.restype = None
@@ -188,6 +190,22 @@ class Context:
                                 _ptr(valid)), "dp_score")
         return (ncc, tex, valid) if want_tex else ncc
 
+    def score_at(self, pos, nrm, ref, nvis, vis, cell_size, normal=None, position=None):
+        """Optimization::GetProjectedTextures(normal, position, textures) + the NCC loop: trial
+        (normal, position) as float64 (n, 3); returns (ncc, tex, valid)."""
+        pos, nrm = (np.ascontiguousarray(a, dtype=np.float32) for a in (pos, nrm))
+        ref, nvis, vis = (np.ascontiguousarray(a, dtype=np.int32) for a in (ref, nvis, vis))
+        n, vs = vis.shape
+        tn = None if normal is None else np.ascontiguousarray(normal, dtype=np.float64)
+        tp = None if position is None else np.ascontiguousarray(position, dtype=np.float64)
+        ncc = np.zeros((n, vs), np.float32)
+        tex = np.zeros((n, vs, cell_size, cell_size, 3), np.uint8)
+        valid = np.zeros((n, vs), np.uint8)
+        s = _soa(pos, nrm, ref, nvis, vis)
+        self._ck(lib().dp_score_at(self._h, C.byref(s), C.c_int(cell_size), _ptr(tn), _ptr(tp),
+                                   _ptr(ncc), _ptr(tex), _ptr(valid)), "dp_score_at")
+        return ncc, tex, valid
+
     def filter(self, pos, nrm, ref, nvis, vis, cell_size):
         pos, nrm = (np.ascontiguousarray(a, dtype=np.float32) for a in (pos, nrm))
         ref = np.ascontiguousarray(ref, dtype=np.int32)
@@ -303,6 +321,16 @@ class Context:
                                          C.byref(gw), C.byref(gh)), "dp_organizer_grid")
         return out
 
+    def organizer_grids(self):
+        """All occupancy grids concatenated in view order (uint8)."""
+        n = C.c_int64(0)
+        self._ck(lib().dp_organizer_grids(self._h, None, C.c_size_t(0), C.byref(n)),
+                 "dp_organizer_grids")
+        out = np.zeros(max(n.value, 1), np.uint8)
+        self._ck(lib().dp_organizer_grids(self._h, _ptr(out), C.c_size_t(out.size), C.byref(n)),
+                 "dp_organizer_grids")
+        return out[:n.value]
+
     def expand(self, cell_size=11, max_levels=-1):
         stats = np.zeros(4, np.int64)
         self._ck(lib().dp_expand(self._h, C.c_int(cell_size), C.c_int(max_levels), _ptr(stats)),
@@ -318,6 +346,22 @@ class Context:
         b, e = C.c_int64(0), C.c_int64(0)
         self._ck(lib().dp_expand_frontier(self._h, C.byref(b), C.byref(e)), "dp_expand_frontier")
         return b.value, e.value
+
+    def expand_last_candidates(self):
+        return int(lib().dp_expand_last_candidates(self._h))
+
+    def expand_frontier_weights(self):
+        w = np.zeros(max(self.num_views(), 1), np.int64)
+        self._ck(lib().dp_expand_frontier_weights(self._h, _ptr(w)), "dp_expand_frontier_weights")
+        return w[:self.num_views()]
+
+    def expand_level_commit_gathered(self, gathered_ptr, world, segment_capacity, counts, stream=0):
+        counts = np.ascontiguousarray(counts, dtype=np.int64)
+        n = C.c_int64(0)
+        self._ck(lib().dp_expand_level_commit_gathered(
+            self._h, C.c_void_p(gathered_ptr), C.c_int(world), C.c_int64(segment_capacity),
+            _ptr(counts), C.byref(n), C.c_void_p(stream)), "dp_expand_level_commit_gathered")
+        return n.value
 
     def expand_level_local(self, cell_size, rank, world, rank_of_view, records_ptr, max_records,
                            stream=0):

@@ -4,8 +4,6 @@
 #include <stdio.h>
 #include <string.h>
 
-#include <cuda.h>  // CUtensorMap types only; the encoder is fetched through the runtime
-
 #include <algorithm>
 
 #include "dp_aux_kernels.cuh"
@@ -27,36 +25,16 @@ int dp_fail(dp_context *ctx, int code, const char *what, cudaError_t e) {
   return code;
 }
 
-// A 2-D tensor map over one packed-BGRx image level: u32 elements, DP_TMA_BOX^2 box, no
-// swizzle, zero fill outside the image.  The driver entry point is resolved through the CUDA
-// runtime so the library does not link libcuda.
-typedef CUresult (*dp_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
-                                       const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
-                                       const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-bool dp_encode_tmap(DpLevel &l) {
-  static dp_encode_tiled_fn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void *p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (dp_encode_tiled_fn)p;
-  }
-  l.has_tmap = false;
-  if (!fn) return false;
-  static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
-  const cuuint64_t dims[2] = {(cuuint64_t)l.pitch_px, (cuuint64_t)l.height};
-  const cuuint64_t strides[1] = {(cuuint64_t)l.pitch_px * 4};
-  const cuuint32_t box[2] = {DP_TMA_BOX, DP_TMA_BOX};
-  const cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(reinterpret_cast<CUtensorMap *>(l.tmap), CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, l.img, dims,
-                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  l.has_tmap = (r == CUDA_SUCCESS);
-  return l.has_tmap;
+int dp_scratch_acquire(dp_context *ctx, cudaStream_t st) {
+  if (ctx->scratch_busy && ctx->scratch_stream != st)
+    DP_CUDA(ctx, cudaStreamWaitEvent(st, ctx->scratch_event, 0));
+  return DP_OK;
+}
+int dp_scratch_release(dp_context *ctx, cudaStream_t st) {
+  DP_CUDA(ctx, cudaEventRecord(ctx->scratch_event, st));
+  ctx->scratch_stream = st;
+  ctx->scratch_busy = true;
+  return DP_OK;
 }
 
 static int npass_for(int s) {
@@ -102,7 +80,7 @@ extern "C" int dp_create(dp_context **out, int device, const dp_params *params) 
     if (cudaGetDevice(&device) != cudaSuccess) return DP_ERR_NO_DEVICE;
   }
   if (device >= count) return DP_ERR_NO_DEVICE;
-  if (cudaSetDevice(device) != cudaSuccess) return DP_ERR_CUDA;
+  DpDeviceGuard guard__(device);
   dp_context *ctx = new dp_context();
   ctx->device = device;
   if (params)
@@ -114,6 +92,11 @@ extern "C" int dp_create(dp_context **out, int device, const dp_params *params) 
     return DP_ERR_INVALID_ARG;
   }
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return DP_ERR_CUDA;
+  }
+  if (cudaEventCreateWithFlags(&ctx->scratch_event, cudaEventDisableTiming) != cudaSuccess) {
+    cudaStreamDestroy(ctx->stream);
     delete ctx;
     return DP_ERR_CUDA;
   }
@@ -133,19 +116,20 @@ static void free_views(dp_context *ctx) {
 
 extern "C" void dp_destroy(dp_context *ctx) {
   if (!ctx) return;
-  cudaSetDevice(ctx->device);
+  DpDeviceGuard guard__(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   free_views(ctx);
-  DpDevBuf *bufs[] = {&ctx->d_views, &ctx->d_tmaps, &ctx->s_pos, &ctx->s_nrm, &ctx->s_ref, &ctx->s_nvis,
+  DpDevBuf *bufs[] = {&ctx->d_views, &ctx->s_pos, &ctx->s_nrm, &ctx->s_ref, &ctx->s_nvis,
                       &ctx->s_vis, &ctx->s_rgb, &ctx->s_ncc, &ctx->s_tex, &ctx->s_valid,
                       &ctx->s_keep, &ctx->s_evals, &ctx->s_xbest, &ctx->s_cand, &ctx->s_ncand,
                       &ctx->s_img, &ctx->s_misc, &ctx->work_counter, &ctx->s_order, &ctx->e_pos, &ctx->e_nrm,
                       &ctx->e_ref, &ctx->e_nvis, &ctx->e_vis, &ctx->e_keep, &ctx->e_seq,
-                      &ctx->e_cells, &ctx->e_flags, &ctx->e_scan, &ctx->e_count, &ctx->org.grid,
+                      &ctx->e_cells, &ctx->e_recs, &ctx->e_flags, &ctx->e_scan, &ctx->e_count, &ctx->org.grid,
                       &ctx->org.claim, &ctx->org.pos, &ctx->org.nrm, &ctx->org.rgb, &ctx->org.ref,
                       &ctx->org.nvis, &ctx->org.vis};
   for (DpDevBuf *b : bufs) b->release();
   for (cudaEvent_t e : ctx->pipe_events) cudaEventDestroy(e);
+  if (ctx->scratch_event) cudaEventDestroy(ctx->scratch_event);
   if (ctx->stream_in) cudaStreamDestroy(ctx->stream_in);
   if (ctx->stream_out) cudaStreamDestroy(ctx->stream_out);
   cudaStreamDestroy(ctx->stream);
@@ -176,7 +160,7 @@ extern "C" int dp_get_params(const dp_context *ctx, dp_params *p) {
 
 extern "C" int dp_sync(dp_context *ctx) {
   if (!ctx) return DP_ERR_INVALID_ARG;
-  cudaSetDevice(ctx->device);
+  DpDeviceGuard guard__(ctx->device);
   DP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return DP_OK;
 }
@@ -220,7 +204,7 @@ static void decompose_projection(const double P[12], double xaxis[3], double cen
 
 extern "C" int dp_set_num_views(dp_context *ctx, int n_views) {
   if (!ctx || n_views < 0 || n_views > 65535) return dp_fail(ctx, DP_ERR_INVALID_ARG, "n_views");
-  cudaSetDevice(ctx->device);
+  DpDeviceGuard guard__(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   free_views(ctx);
   ctx->views.resize(n_views);
@@ -240,7 +224,7 @@ extern "C" int dp_upload_view(dp_context *ctx, int view_id, const double P[12], 
     return dp_fail(ctx, DP_ERR_INVALID_ARG, "view_id out of range (call dp_set_num_views)");
   if (!P || !bgr || width <= 0 || height <= 0 || stride < (size_t)width * 3)
     return dp_fail(ctx, DP_ERR_INVALID_ARG, "dp_upload_view arguments");
-  cudaSetDevice(ctx->device);
+  DpDeviceGuard guard__(ctx->device);
   DpViewHost &v = ctx->views[view_id];
   for (auto &l : v.levels)
     if (l.img) cudaFree(l.img);
@@ -258,10 +242,11 @@ extern "C" int dp_upload_view(dp_context *ctx, int view_id, const double P[12], 
   l.pitch_px = (width + 31) & ~31;  // 128-byte aligned rows
   // one spare row: the texel pass may read (never use) the right / lower neighbour of an edge pixel
   DP_CUDA(ctx, cudaMalloc(&l.img, (size_t)l.pitch_px * (height + 1) * sizeof(uint32_t)));
+  v.levels.push_back(l);  // owned by the view from here on: freed by free_views / the next upload
+  v.set = false;
   DP_CUDA(ctx, cudaMemsetAsync(l.img + (size_t)l.pitch_px * height, 0, (size_t)l.pitch_px * 4, ctx->stream));
-  dp_encode_tmap(l);
-  v.levels.push_back(l);
   const size_t bytes = stride * (size_t)height;
+  // (the staging buffer is reused by the next upload, hence the synchronisation below)
   DP_CUDA(ctx, ctx->s_img.ensure(bytes));
   DP_CUDA(ctx, cudaMemcpyAsync(ctx->s_img.ptr, bgr, bytes, cudaMemcpyHostToDevice, ctx->stream));
   dim3 grid((l.pitch_px + 255) / 256, height);
@@ -298,8 +283,6 @@ int dp_sync_views(dp_context *ctx) {
   const int nv = (int)ctx->views.size();
   if (nv == 0) return dp_fail(ctx, DP_ERR_STATE, "no views uploaded");
   std::vector<DpViewDev> h(nv);
-  std::vector<unsigned char> tm((size_t)nv * 128);
-  DP_CUDA(ctx, ctx->d_tmaps.ensure((size_t)nv * 128));
   long long off = 0;
   for (int i = 0; i < nv; ++i) {
     const DpViewHost &v = ctx->views[i];
@@ -315,8 +298,6 @@ int dp_sync_views(dp_context *ctx) {
       h[i].center[j] = v.center[j];
     }
     h[i].img = l.img;
-    memcpy(tm.data() + (size_t)i * 128, l.tmap, 128);
-    h[i].tmap = l.has_tmap ? (const void *)(ctx->d_tmaps.as<unsigned char>() + (size_t)i * 128) : nullptr;
     h[i].width = l.width;
     h[i].height = l.height;
     h[i].pitch_px = l.pitch_px;
@@ -328,8 +309,6 @@ int dp_sync_views(dp_context *ctx) {
   DP_CUDA(ctx, ctx->d_views.ensure(sizeof(DpViewDev) * nv));
   DP_CUDA(ctx, cudaMemcpyAsync(ctx->d_views.ptr, h.data(), sizeof(DpViewDev) * nv,
                                cudaMemcpyHostToDevice, ctx->stream));
-  DP_CUDA(ctx, cudaMemcpyAsync(ctx->d_tmaps.ptr, tm.data(), tm.size(), cudaMemcpyHostToDevice,
-                               ctx->stream));
   DP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->org.n_cells = off;
   ctx->views_dirty = false;
@@ -429,19 +408,23 @@ static int launch_score(dp_context *ctx, const DpScoreArgs &a, int cell_size, cu
   return DP_OK;
 }
 
-extern "C" int dp_score_dev(dp_context *ctx, const dp_patch_dev *p, int cell_size, float *ncc,
-                            uint8_t *tex, uint8_t *valid, void *stream) {
+extern "C" int dp_score_at_dev(dp_context *ctx, const dp_patch_dev *p, int cell_size,
+                               const double *normal, const double *position, float *ncc,
+                               uint8_t *tex, uint8_t *valid, void *stream) {
   int rc = check_patch_dev(ctx, p, cell_size);
   if (rc != DP_OK) return rc;
   if (p->n == 0) return DP_OK;
-  cudaSetDevice(ctx->device);
+  DpDeviceGuard guard__(ctx->device);
   if ((rc = dp_sync_views(ctx)) != DP_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = dp_scratch_acquire(ctx, st)) != DP_OK) return rc;
   DpScoreArgs a;
   a.p = patch_args(ctx, p, cell_size);
   a.ncc = ncc;
   a.tex = tex;
   a.valid = valid;
+  a.trial_nrm = normal;
+  a.trial_pos = position;
   a.thr = 0;
   a.min_visible = 0;
   a.keep = nullptr;
@@ -455,7 +438,12 @@ extern "C" int dp_score_dev(dp_context *ctx, const dp_patch_dev *p, int cell_siz
   }
   if (rc != DP_OK) return rc;
   DP_CUDA(ctx, cudaGetLastError());
-  return DP_OK;
+  return dp_scratch_release(ctx, st);
+}
+
+extern "C" int dp_score_dev(dp_context *ctx, const dp_patch_dev *p, int cell_size, float *ncc,
+                            uint8_t *tex, uint8_t *valid, void *stream) {
+  return dp_score_at_dev(ctx, p, cell_size, nullptr, nullptr, ncc, tex, valid, stream);
 }
 
 extern "C" int dp_filter_dev(dp_context *ctx, dp_patch_dev *p, int cell_size, uint8_t *keep,
@@ -464,19 +452,21 @@ extern "C" int dp_filter_dev(dp_context *ctx, dp_patch_dev *p, int cell_size, ui
   if (rc != DP_OK) return rc;
   if (!keep) return dp_fail(ctx, DP_ERR_INVALID_ARG, "keep is null");
   if (p->n == 0) return DP_OK;
-  cudaSetDevice(ctx->device);
+  DpDeviceGuard guard__(ctx->device);
   if ((rc = dp_sync_views(ctx)) != DP_OK) return rc;
+  if ((rc = dp_scratch_acquire(ctx, (cudaStream_t)stream)) != DP_OK) return rc;
   DpScoreArgs a;
   a.p = patch_args(ctx, p, cell_size);
   a.ncc = nullptr;
   a.tex = nullptr;
   a.valid = nullptr;
+  a.trial_nrm = a.trial_pos = nullptr;
   a.thr = ctx->prm.score_threshold;
   a.min_visible = ctx->prm.minimum_visible_image;
   a.keep = keep;
   if ((rc = launch_score<false, true>(ctx, a, cell_size, (cudaStream_t)stream)) != DP_OK) return rc;
   DP_CUDA(ctx, cudaGetLastError());
-  return DP_OK;
+  return dp_scratch_release(ctx, (cudaStream_t)stream);
 }
 
 template <int NPASS>
@@ -514,9 +504,10 @@ extern "C" int dp_refine_dev(dp_context *ctx, dp_patch_dev *p, int cell_size, co
   int rc = check_patch_dev(ctx, p, cell_size);
   if (rc != DP_OK) return rc;
   if (p->n == 0) return DP_OK;
-  cudaSetDevice(ctx->device);
+  DpDeviceGuard guard__(ctx->device);
   if ((rc = dp_sync_views(ctx)) != DP_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = dp_scratch_acquire(ctx, st)) != DP_OK) return rc;
   DP_CUDA(ctx, ctx->work_counter.ensure(sizeof(unsigned int)));
   DP_CUDA(ctx, cudaMemsetAsync(ctx->work_counter.ptr, 0, sizeof(unsigned int), st));
   DpRefineArgs a;
@@ -551,7 +542,7 @@ extern "C" int dp_refine_dev(dp_context *ctx, dp_patch_dev *p, int cell_size, co
   }
   ++ctx->launches;
   DP_CUDA(ctx, e);
-  return DP_OK;
+  return dp_scratch_release(ctx, st);
 }
 
 extern "C" int dp_visibility_dev(dp_context *ctx, dp_patch_dev *p, int32_t *ncand, int32_t *cand,
@@ -561,7 +552,7 @@ extern "C" int dp_visibility_dev(dp_context *ctx, dp_patch_dev *p, int32_t *ncan
   if (p->n == 0) return DP_OK;
   if (!p->pos || !p->nrm || !p->ref || !p->nvis || !p->vis)
     return dp_fail(ctx, DP_ERR_INVALID_ARG, "null patch array");
-  cudaSetDevice(ctx->device);
+  DpDeviceGuard guard__(ctx->device);
   int rc = dp_sync_views(ctx);
   if (rc != DP_OK) return rc;
   const long long threads = (long long)p->n * 32;
@@ -578,7 +569,7 @@ extern "C" int dp_color_dev(dp_context *ctx, dp_patch_dev *p, void *stream) {
   if (!ctx || !p) return DP_ERR_INVALID_ARG;
   if (p->n == 0) return DP_OK;
   if (p->n < 0 || !p->pos || !p->rgb) return dp_fail(ctx, DP_ERR_INVALID_ARG, "dp_color arguments");
-  cudaSetDevice(ctx->device);
+  DpDeviceGuard guard__(ctx->device);
   int rc = dp_sync_views(ctx);
   if (rc != DP_OK) return rc;
   const long long threads = (long long)p->n * 32;
@@ -601,7 +592,7 @@ static int upload_patches(dp_context *ctx, const dp_patch_soa *h, dp_patch_dev *
   if (h->n < 0 || h->vstride <= 0) return dp_fail(ctx, DP_ERR_INVALID_ARG, "patch batch shape");
   if (h->n > 0 && (!h->pos || !h->nrm || !h->ref || !h->nvis || !h->vis))
     return dp_fail(ctx, DP_ERR_INVALID_ARG, "null patch array");
-  cudaSetDevice(ctx->device);
+  DpDeviceGuard guard__(ctx->device);
   const size_t n = (size_t)h->n, vs = (size_t)h->vstride;
   DP_CUDA(ctx, ctx->s_pos.ensure(n * 12));
   DP_CUDA(ctx, ctx->s_nrm.ensure(n * 12));
@@ -627,8 +618,9 @@ static int upload_patches(dp_context *ctx, const dp_patch_soa *h, dp_patch_dev *
   return DP_OK;
 }
 
-extern "C" int dp_score(dp_context *ctx, const dp_patch_soa *h, int cell_size, float *ncc,
-                        uint8_t *tex, uint8_t *valid) {
+extern "C" int dp_score_at(dp_context *ctx, const dp_patch_soa *h, int cell_size,
+                           const double *normal, const double *position, float *ncc, uint8_t *tex,
+                           uint8_t *valid) {
   if (!ctx) return DP_ERR_INVALID_ARG;
   if (!ncc) return dp_fail(ctx, DP_ERR_INVALID_ARG, "ncc is null");
   dp_patch_dev d;
@@ -640,8 +632,23 @@ extern "C" int dp_score(dp_context *ctx, const dp_patch_soa *h, int cell_size, f
   DP_CUDA(ctx, ctx->s_ncc.ensure(nv * 4));
   if (tex) DP_CUDA(ctx, ctx->s_tex.ensure(nv * tb));
   if (valid) DP_CUDA(ctx, ctx->s_valid.ensure(nv));
-  rc = dp_score_dev(ctx, &d, cell_size, ctx->s_ncc.as<float>(), tex ? ctx->s_tex.as<uint8_t>() : nullptr,
-                    valid ? ctx->s_valid.as<uint8_t>() : nullptr, ctx->stream);
+  const double *d_tn = nullptr, *d_tp = nullptr;
+  if (normal || position) {
+    const size_t b3 = (size_t)h->n * 24;
+    DP_CUDA(ctx, ctx->s_xbest.ensure(2 * b3));
+    if (normal) {
+      DP_CUDA(ctx, cudaMemcpyAsync(ctx->s_xbest.ptr, normal, b3, cudaMemcpyHostToDevice, ctx->stream));
+      d_tn = ctx->s_xbest.as<double>();
+    }
+    if (position) {
+      DP_CUDA(ctx, cudaMemcpyAsync(ctx->s_xbest.as<char>() + b3, position, b3, cudaMemcpyHostToDevice,
+                                   ctx->stream));
+      d_tp = ctx->s_xbest.as<double>() + 3 * (size_t)h->n;
+    }
+  }
+  rc = dp_score_at_dev(ctx, &d, cell_size, d_tn, d_tp, ctx->s_ncc.as<float>(),
+                       tex ? ctx->s_tex.as<uint8_t>() : nullptr,
+                       valid ? ctx->s_valid.as<uint8_t>() : nullptr, ctx->stream);
   if (rc != DP_OK) return rc;
   cudaStream_t st = ctx->stream;
   DP_CUDA(ctx, cudaMemcpyAsync(ncc, ctx->s_ncc.ptr, nv * 4, cudaMemcpyDeviceToHost, st));
@@ -649,6 +656,11 @@ extern "C" int dp_score(dp_context *ctx, const dp_patch_soa *h, int cell_size, f
   if (valid) DP_CUDA(ctx, cudaMemcpyAsync(valid, ctx->s_valid.ptr, nv, cudaMemcpyDeviceToHost, st));
   DP_CUDA(ctx, cudaStreamSynchronize(st));
   return DP_OK;
+}
+
+extern "C" int dp_score(dp_context *ctx, const dp_patch_soa *h, int cell_size, float *ncc,
+                        uint8_t *tex, uint8_t *valid) {
+  return dp_score_at(ctx, h, cell_size, nullptr, nullptr, ncc, tex, valid);
 }
 
 extern "C" int dp_filter(dp_context *ctx, dp_patch_soa *h, int cell_size, uint8_t *keep) {
@@ -718,7 +730,7 @@ extern "C" int dp_filter_refine(dp_context *ctx, dp_patch_soa *h, int cell_size,
     return dp_fail(ctx, DP_ERR_INVALID_ARG, "null patch array");
   int rc = check_patch_dev_args(ctx, cell_size);
   if (rc != DP_OK) return rc;
-  cudaSetDevice(ctx->device);
+  DpDeviceGuard guard__(ctx->device);
   if ((rc = dp_sync_views(ctx)) != DP_OK) return rc;
   const size_t n = (size_t)h->n, vs = (size_t)h->vstride;
   DP_CUDA(ctx, ctx->s_pos.ensure(n * 12));
@@ -748,31 +760,33 @@ extern "C" int dp_filter_refine(dp_context *ctx, dp_patch_soa *h, int cell_size,
   int32_t *d_ref = ctx->s_ref.as<int32_t>(), *d_nvis = ctx->s_nvis.as<int32_t>(),
           *d_vis = ctx->s_vis.as<int32_t>(), *d_evals = ctx->s_evals.as<int32_t>();
   uint8_t *d_keep = ctx->s_keep.as<uint8_t>();
-  for (size_t c = 0; c < n_chunks; ++c) {
-    const size_t o = c * chunk, m = std::min(chunk, n - o);
-    DP_CUDA(ctx, cudaMemcpyAsync(d_pos + 3 * o, h->pos + 3 * o, m * 12, cudaMemcpyHostToDevice, s_in));
-    DP_CUDA(ctx, cudaMemcpyAsync(d_nrm + 3 * o, h->nrm + 3 * o, m * 12, cudaMemcpyHostToDevice, s_in));
-    DP_CUDA(ctx, cudaMemcpyAsync(d_ref + o, h->ref + o, m * 4, cudaMemcpyHostToDevice, s_in));
-    DP_CUDA(ctx, cudaMemcpyAsync(d_nvis + o, h->nvis + o, m * 4, cudaMemcpyHostToDevice, s_in));
-    DP_CUDA(ctx, cudaMemcpyAsync(d_vis + o * vs, h->vis + o * vs, m * vs * 4, cudaMemcpyHostToDevice, s_in));
-    DP_CUDA(ctx, cudaEventRecord(ctx->pipe_events[2 * c], s_in));
-  }
-  int first_rc = DP_OK;
-  dp_patch_dev d;
-  d.vstride = h->vstride;
-  d.rgb = nullptr;
-  for (size_t c = 0; c < n_chunks && first_rc == DP_OK; ++c) {
-    const size_t o = c * chunk, m = std::min(chunk, n - o);
-    d.n = (int32_t)m;
-    d.pos = d_pos + 3 * o;
-    d.nrm = d_nrm + 3 * o;
-    d.ref = d_ref + o;
-    d.nvis = d_nvis + o;
-    d.vis = d_vis + o * vs;
-    DP_CUDA(ctx, cudaStreamWaitEvent(s_cmp, ctx->pipe_events[2 * c], 0));
-    first_rc = dp_filter_dev(ctx, &d, cell_size, d_keep + o, s_cmp);
-  }
-  if (first_rc == DP_OK) {
+  // Every failure below funnels to the common exit: no copy into or out of the caller's arrays
+  // may still be in flight when this function returns.
+  auto body = [&]() -> int {
+    for (size_t c = 0; c < n_chunks; ++c) {
+      const size_t o = c * chunk, m = std::min(chunk, n - o);
+      DP_CUDA(ctx, cudaMemcpyAsync(d_pos + 3 * o, h->pos + 3 * o, m * 12, cudaMemcpyHostToDevice, s_in));
+      DP_CUDA(ctx, cudaMemcpyAsync(d_nrm + 3 * o, h->nrm + 3 * o, m * 12, cudaMemcpyHostToDevice, s_in));
+      DP_CUDA(ctx, cudaMemcpyAsync(d_ref + o, h->ref + o, m * 4, cudaMemcpyHostToDevice, s_in));
+      DP_CUDA(ctx, cudaMemcpyAsync(d_nvis + o, h->nvis + o, m * 4, cudaMemcpyHostToDevice, s_in));
+      DP_CUDA(ctx, cudaMemcpyAsync(d_vis + o * vs, h->vis + o * vs, m * vs * 4, cudaMemcpyHostToDevice, s_in));
+      DP_CUDA(ctx, cudaEventRecord(ctx->pipe_events[2 * c], s_in));
+    }
+    dp_patch_dev d;
+    d.vstride = h->vstride;
+    d.rgb = nullptr;
+    for (size_t c = 0; c < n_chunks; ++c) {
+      const size_t o = c * chunk, m = std::min(chunk, n - o);
+      d.n = (int32_t)m;
+      d.pos = d_pos + 3 * o;
+      d.nrm = d_nrm + 3 * o;
+      d.ref = d_ref + o;
+      d.nvis = d_nvis + o;
+      d.vis = d_vis + o * vs;
+      DP_CUDA(ctx, cudaStreamWaitEvent(s_cmp, ctx->pipe_events[2 * c], 0));
+      const int frc = dp_filter_dev(ctx, &d, cell_size, d_keep + o, s_cmp);
+      if (frc != DP_OK) return frc;
+    }
     DP_CUDA(ctx, cudaEventRecord(ctx->pipe_events[1], s_cmp));  // filter done
     DP_CUDA(ctx, cudaStreamWaitEvent(s_out, ctx->pipe_events[1], 0));
     DP_CUDA(ctx, cudaMemcpyAsync(keep, d_keep, n, cudaMemcpyDeviceToHost, s_out));
@@ -784,19 +798,27 @@ extern "C" int dp_filter_refine(dp_context *ctx, dp_patch_soa *h, int cell_size,
     d.ref = d_ref;
     d.nvis = d_nvis;
     d.vis = d_vis;
-    first_rc = dp_refine_dev(ctx, &d, cell_size, d_keep, evals ? d_evals : nullptr, nullptr, s_cmp);
-  }
-  if (first_rc == DP_OK) {
+    const int rrc = dp_refine_dev(ctx, &d, cell_size, d_keep, evals ? d_evals : nullptr, nullptr, s_cmp);
+    if (rrc != DP_OK) return rrc;
     DP_CUDA(ctx, cudaEventRecord(ctx->pipe_events[3], s_cmp));  // refine done
     DP_CUDA(ctx, cudaStreamWaitEvent(s_out, ctx->pipe_events[3], 0));
     DP_CUDA(ctx, cudaMemcpyAsync(h->pos, d_pos, n * 12, cudaMemcpyDeviceToHost, s_out));
     DP_CUDA(ctx, cudaMemcpyAsync(h->nrm, d_nrm, n * 12, cudaMemcpyDeviceToHost, s_out));
     if (evals) DP_CUDA(ctx, cudaMemcpyAsync(evals, d_evals, n * 4, cudaMemcpyDeviceToHost, s_out));
+    return DP_OK;
+  };
+  const int first_rc = body();
+  const std::string first_err = ctx->err;
+  const cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(s_cmp),
+                    e3 = cudaStreamSynchronize(s_out);
+  if (first_rc != DP_OK) {
+    ctx->err = first_err;
+    return first_rc;
   }
-  DP_CUDA(ctx, cudaStreamSynchronize(s_in));
-  DP_CUDA(ctx, cudaStreamSynchronize(s_cmp));
-  DP_CUDA(ctx, cudaStreamSynchronize(s_out));
-  return first_rc;
+  DP_CUDA(ctx, e1);
+  DP_CUDA(ctx, e2);
+  DP_CUDA(ctx, e3);
+  return DP_OK;
 }
 
 extern "C" int dp_visibility(dp_context *ctx, dp_patch_soa *h, int32_t *ncand, int32_t *cand) {
@@ -825,7 +847,7 @@ extern "C" int dp_color(dp_context *ctx, dp_patch_soa *h) {
   if (h->n < 0 || (h->n > 0 && (!h->pos || !h->rgb)))
     return dp_fail(ctx, DP_ERR_INVALID_ARG, "dp_color arguments");
   if (h->n == 0) return DP_OK;
-  cudaSetDevice(ctx->device);
+  DpDeviceGuard guard__(ctx->device);
   const size_t n = (size_t)h->n;
   DP_CUDA(ctx, ctx->s_pos.ensure(n * 12));
   DP_CUDA(ctx, ctx->s_rgb.ensure(n * 3));

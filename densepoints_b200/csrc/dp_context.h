@@ -31,11 +31,23 @@ struct DpDevBuf {  // grow-only device scratch
   T *as() const { return reinterpret_cast<T *>(ptr); }
 };
 
+// Every entry point runs on the context's device and leaves the caller's current device as it
+// found it.
+struct DpDeviceGuard {
+  int prev = -1;
+  explicit DpDeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DpDeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 struct DpLevel {  // one pyramid level of one view
   uint32_t *img = nullptr;
   int width = 0, height = 0, pitch_px = 0;
-  alignas(64) unsigned char tmap[128];  // CUtensorMap: u32 [height][pitch_px], 16x16 box
-  bool has_tmap = false;
 };
 
 struct DpViewHost {
@@ -53,7 +65,8 @@ struct DpOrganizer {
   long long n_cells = 0;
   DpDevBuf grid;               // u8 occupancy count per cell, all views concatenated
   DpDevBuf claim;              // u32 min sequence id claiming each cell in the current round
-  // store (SoA), capacity `cap` patches, vstride = n_views
+  // store (SoA), capacity `cap` patches; vstride = n_views; vis = the visible sets as bit
+  // masks, ceil(n_views / 32) u32 words per patch (ascending view order is implicit)
   long long n = 0, cap = 0;
   int vstride = 0;
   DpDevBuf pos, nrm, rgb, ref, nvis, vis;
@@ -69,7 +82,6 @@ struct dp_context {
   dp_params prm;
   std::vector<DpViewHost> views;
   DpDevBuf d_views;      // DpViewDev[n_views] of the active level
-  DpDevBuf d_tmaps;      // CUtensorMap[n_views] of the active level (128 B each)
   bool views_dirty = true;
   int level = 0;
   int n_levels = 1;
@@ -79,8 +91,15 @@ struct dp_context {
   DpDevBuf s_pos, s_nrm, s_ref, s_nvis, s_vis, s_rgb, s_ncc, s_tex, s_valid, s_keep, s_evals,
       s_xbest, s_cand, s_ncand, s_img, s_misc;
   DpDevBuf work_counter, s_order;
+  // The dp_*_dev calls share the scratch above and below (work counter, order table, expansion
+  // buffers).  Calls on different streams are therefore chained: a call first makes its stream
+  // wait for the event the previous call recorded on its own stream (dp_scratch_acquire /
+  // dp_scratch_release), so two asynchronous calls never use the scratch at the same time.
+  cudaEvent_t scratch_event = nullptr;
+  cudaStream_t scratch_stream = nullptr;
+  bool scratch_busy = false;
   // expansion scratch
-  DpDevBuf e_pos, e_nrm, e_ref, e_nvis, e_vis, e_keep, e_seq, e_cells, e_flags, e_scan, e_count;
+  DpDevBuf e_pos, e_nrm, e_ref, e_nvis, e_vis, e_keep, e_seq, e_cells, e_recs, e_flags, e_scan, e_count;
   DpOrganizer org;
   long long org_last_candidates = 0;
   int sm_count = 148;
@@ -89,7 +108,9 @@ struct dp_context {
 // internal helpers shared by the translation units
 int dp_fail(dp_context *ctx, int code, const char *what, cudaError_t e = cudaSuccess);
 int dp_sync_views(dp_context *ctx);
-bool dp_encode_tmap(DpLevel &l);  // fills l.tmap (cuTensorMapEncodeTiled via the runtime)  // (re)builds the DpViewDev table for the active level
+int dp_scratch_acquire(dp_context *ctx, cudaStream_t st);
+int dp_scratch_release(dp_context *ctx, cudaStream_t st);
+// (dp_sync_views (re)builds the DpViewDev table for the active level)
 #define DP_CUDA(ctx, call)                                             \
   do {                                                                 \
     cudaError_t e__ = (call);                                          \

@@ -25,7 +25,6 @@ struct DpViewDev {
   double xa[3];      // View::GetXAxis().normalized()
   double center[3];  // View::GetCameraCenter()
   const uint32_t *img;  // packed BGRx, pitch_px pixels per row
-  const void *tmap;     // CUtensorMap (global memory): 2-D u32 tensor, DP_TMA_BOX^2 box; or null
   int width, height, pitch_px;
   int gw, gh;              // PatchGrid dims: width / grid_scale, height / grid_scale
   long long grid_off;      // offset of this view's grid in the occupancy array
@@ -69,14 +68,19 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
 
 // Per-patch frame: scaled patch axes in world units (optimization.cpp:19-30).
 struct DpFrame {
-  double p[3];   // patch centre
+  double p[3];   // centre of the four corners = patch_.GetPosition(), the STORED position
+                 // (patch.cpp:119-123), whatever (normal, position) GetProjectedTextures got
   double ax[3];  // scale * x_axis
   double ay[3];  // scale * y_axis (y = n x x, not normalised, patch.cpp:96)
   bool ok;       // false when dx == 0 (LOG(FATAL) in the reference, optimization.cpp:27)
 };
 
+// n, p: the (normal, position) ARGUMENTS of GetProjectedTextures -- they only feed
+// GetProjectedXYAxisAndScale (optimization.cpp:24-26: y axis and dx); pc: the stored position.
+// During Optimize() p is the trial position, so a trial depth rescales the quad around pc.
 __device__ __forceinline__ void dp_make_frame(const DpViewDev *__restrict__ ref, int s,
-                                              const double n[3], const double p[3], DpFrame &f) {
+                                              const double n[3], const double p[3],
+                                              const double pc[3], DpFrame &f) {
   const double xa0 = ref->xa[0], xa1 = ref->xa[1], xa2 = ref->xa[2];
   // y_axis = normal.cross(x_axis)
   double ya0 = xsub(xmul(n[1], xa2), xmul(n[2], xa1));
@@ -89,7 +93,7 @@ __device__ __forceinline__ void dp_make_frame(const DpViewDev *__restrict__ ref,
   double dx = sqrt(xadd(xmul(du, du), xmul(dv, dv)));
   f.ok = (dx != 0.0) && isfinite(dx);
   double scale = (double)(s / 2) / dx;  // integer cell_size / 2 (optimization.cpp:30)
-  f.p[0] = p[0]; f.p[1] = p[1]; f.p[2] = p[2];
+  f.p[0] = pc[0]; f.p[1] = pc[1]; f.p[2] = pc[2];
   f.ax[0] = xmul(scale, xa0); f.ax[1] = xmul(scale, xa1); f.ax[2] = xmul(scale, xa2);
   f.ay[0] = xmul(scale, ya0); f.ay[1] = xmul(scale, ya1); f.ay[2] = xmul(scale, ya2);
 }
@@ -143,14 +147,12 @@ struct __align__(16) DpViewSetup {
   double M[8];          // source = (M0 x + M1 y + M2, M3 x + M4 y + M5) / (M6 x + M7 y + 1),
                         // in 1/32-px units (pre-scaled by INTER_TAB_SIZE), relative to the ROI
   const uint32_t *src;  // first pixel of the ROI (packed BGRx)
-  const void *tmap;     // tensor map of the view when the ROI fits one TMA box, else null
   int pitch, rw, rh;    // image pitch (pixels), ROI width / height
   int ok;               // 0 where the reference pushes an empty cv::Mat
   int lgp;              // log2 of the staged tile's row pitch (next power of two >= rw)
-  int tlx, tly;         // TMA tile coordinates: tlx is the ROI origin rounded down to 4 px
-  int xoff;             // ROI origin - tlx (0..3): column of the ROI inside the staged tile
+  int pad_;
 };
-static_assert(sizeof(DpViewSetup) == 112, "DpViewSetup layout");
+static_assert(sizeof(DpViewSetup) == 96, "DpViewSetup layout");
 
 // The same record without the TMA / generic-staging fields, for the group kernels (dp_group.cuh):
 // 80 bytes.  M2 and M5 are 32 x (an fp32 number), exactly representable in fp32.
@@ -162,61 +164,13 @@ struct __align__(16) DpViewSetupG {
 };
 static_assert(sizeof(DpViewSetupG) == 80, "DpViewSetupG layout");
 
-// ---- TMA (cp.async.bulk.tensor) staging of a patch footprint -----------------------------
-// A footprint of up to DP_TMA_BOX x DP_TMA_BOX pixels is tile-local: one elected lane issues
-// a single 2-D tensor copy of a fixed box anchored at the ROI origin (out-of-image elements
-// are zero-filled and never read) and the warp waits on an mbarrier; the copy of the next
-// view is issued before the current view is computed, so its latency is hidden.
-// Measured on B200 (tools/probe/tma_probe2.cu): the innermost tile coordinate times the
-// element size must be a multiple of 16 bytes, otherwise the copy raises "illegal
-// instruction" -- so the box starts at the ROI origin rounded down to 4 pixels.
-#define DP_TMA_BOX 16
-#define DP_TMA_LGP 4
-#define DP_TMA_BYTES (DP_TMA_BOX * DP_TMA_BOX * 4)
-
 __device__ __forceinline__ uint32_t dp_smem_u32(const void *p) {
   return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void dp_mbar_init(uint64_t *bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dp_smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void dp_mbar_init_fence() {
-  // make the initialised barrier visible to the async (TMA) proxy; CTA scope is enough (a
-  // cluster-scope fence would also invalidate L1 at every CTA start)
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void dp_tma_load_tile(uint32_t *dst, const void *tmap, int x, int y,
-                                                 uint64_t *bar) {
-  const uint32_t b = dp_smem_u32(bar);
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b),
-               "r"((unsigned)DP_TMA_BYTES)
-               : "memory");
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
-      "[%0], [%1, {%2, %3}], [%4];" ::"r"(dp_smem_u32(dst)),
-      "l"(tmap), "r"(x), "r"(y), "r"(b)
-      : "memory");
-}
-__device__ __forceinline__ void dp_mbar_wait(uint64_t *bar, unsigned parity) {
-  const uint32_t b = dp_smem_u32(bar);
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(b), "r"(parity)
-        : "memory");
-  } while (!done);
 }
 
 __device__ __forceinline__ void dp_write_setup(DpViewSetup &R, double m0, double m1, double m2,
                                                double m3, double m4, double m5, double m6, double m7,
-                                               const uint32_t *src, int pitch, int rw, int rh, bool ok,
-                                               const void *tmap, int tlx, int tly) {
+                                               const uint32_t *src, int pitch, int rw, int rh, bool ok) {
   R.M[0] = m0; R.M[1] = m1; R.M[2] = m2; R.M[3] = m3;
   R.M[4] = m4; R.M[5] = m5; R.M[6] = m6; R.M[7] = m7;
   R.src = src;
@@ -224,18 +178,12 @@ __device__ __forceinline__ void dp_write_setup(DpViewSetup &R, double m0, double
   R.rw = rw;
   R.rh = rh;
   R.ok = ok ? 1 : 0;
-  const int xoff = tlx & 3;
-  const bool fits = ok && tmap != nullptr && rw + xoff <= DP_TMA_BOX && rh <= DP_TMA_BOX;
-  R.tmap = fits ? tmap : nullptr;
-  R.lgp = fits ? DP_TMA_LGP : 32 - __clz(max(rw, 1) - 1);  // ceil(log2(rw))
-  R.tlx = tlx - xoff;
-  R.tly = tly;
-  R.xoff = fits ? xoff : 0;
+  R.lgp = 32 - __clz(max(rw, 1) - 1);  // ceil(log2(rw))
+  R.pad_ = 0;
 }
 __device__ __forceinline__ void dp_write_setup(DpViewSetupG &R, double m0, double m1, double m2,
                                                double m3, double m4, double m5, double m6, double m7,
-                                               const uint32_t *src, int pitch, int rw, int rh, bool ok,
-                                               const void *, int, int) {
+                                               const uint32_t *src, int pitch, int rw, int rh, bool ok) {
   R.M0 = m0; R.M1 = m1; R.M3 = m3; R.M4 = m4; R.M6 = m6; R.M7 = m7;
   R.M2 = (float)m2;
   R.M5 = (float)m5;
@@ -255,8 +203,7 @@ __device__ __forceinline__ void dp_write_setup(DpViewSetupG &R, double m0, doubl
 template <int GL = 32, typename REC = DpViewSetup>
 __device__ __forceinline__ void dp_setup_views(const DpViewDev *__restrict__ views, int n_views,
                                                const int32_t *vis, int kcount, int kcmax, int s,
-                                               const DpFrame &f, REC *recs, int lane,
-                                               bool use_tma) {
+                                               const DpFrame &f, REC *recs, int lane) {
   const int c = lane & 3, slot = (lane & (GL - 1)) >> 2;
   const double sgx = (c == 1 || c == 2) ? 1.0 : -1.0;  // corners (-,-) (+,-) (+,+) (-,+),
   const double sgy = (c >= 2) ? 1.0 : -1.0;            // patch.cpp:119-123
@@ -315,8 +262,7 @@ __device__ __forceinline__ void dp_setup_views(const DpViewDev *__restrict__ vie
                        isfinite(m7);
       const bool ok = all_in && rw > 0 && rh > 0 && (den != 0.0) && fin;  // optimization.cpp:45
       dp_write_setup(recs[k], m0, m1, 32.0 * qx0, m3, m4, 32.0 * qy0, m6, m7,
-                     V->img + (ok ? (size_t)tly * V->pitch_px + tlx : 0), V->pitch_px, rw, rh, ok,
-                     use_tma ? V->tmap : nullptr, tlx, tly);
+                     V->img + (ok ? (size_t)tly * V->pitch_px + tlx : 0), V->pitch_px, rw, rh, ok);
     }
   }
 }
@@ -324,8 +270,7 @@ __device__ __forceinline__ void dp_setup_views(const DpViewDev *__restrict__ vie
 // ---------------------------------------------------------------------------------------
 // Phase B: the texture of one view from its set-up record: gray value of every texel owned
 // by this lane (g[j], 0..255), optionally the BGR texels themselves.  `tile` is this warp's
-// shared-memory staging buffer of tile_cap pixels; with pre_staged the ROI is already there
-// (TMA, row pitch 2^R.lgp).
+// shared-memory staging buffer of tile_cap pixels (row pitch 2^R.lgp).
 
 // Generic staging: tile rows padded to a power-of-two pitch so the flat index splits with a
 // shift and a mask; each 32-lane step loads 32/pitch whole rows with 32-bit loads.
@@ -362,7 +307,7 @@ template <int NPASS, bool WRITE_TEX, bool staged, int GL = 32, typename TX = DpT
 __device__ __forceinline__ void dp_view_texture(const DpViewSetup &R, int npx, const TX &tx,
                                                 const uint32_t *tile0, int lane, int (&g)[NPASS],
                                                 uint8_t *__restrict__ tex_out) {
-  const uint32_t *tile = tile0 + R.xoff;
+  const uint32_t *tile = tile0;
   const double M0 = R.M[0], M1 = R.M[1], M2 = R.M[2], M3 = R.M[3], M4 = R.M[4], M5 = R.M[5],
                M6 = R.M[6], M7 = R.M[7];
   const uint32_t *__restrict__ src = R.src;

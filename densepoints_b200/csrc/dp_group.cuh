@@ -469,11 +469,12 @@ template <typename C, bool WRITE_TEX, typename Sink>
 __device__ __forceinline__ void dp_eval_views_g(const DpViewDev *__restrict__ views, int n_views,
                                                 int ref, bool ref_ok, const int32_t *vis, int nv,
                                                 int s, int npx, const double n[3], const double p[3],
+                                                const double pc[3],
                                                 DpViewSetupG *recs, const double2 *txy, uint8_t *gs,
                                                 uint32_t *tile, int lane, const DpGroupLane &L,
                                                 uint8_t *tex_base, uint8_t *valid_base, Sink sink) {
   DpFrame f;
-  dp_make_frame(views + (ref_ok ? ref : 0), s, n, p, f);
+  dp_make_frame(views + (ref_ok ? ref : 0), s, n, p, pc, f);
   if (!ref_ok) f.ok = false;  // every texture empty (optimization.cpp:45)
   constexpr int NP = C::NP, GL = C::GL, GROUND = C::GROUND;
   const double scale = 1.0 / (double)npx;  // cv::meanStdDev: mean = sum * (1/N)
@@ -486,7 +487,7 @@ __device__ __forceinline__ void dp_eval_views_g(const DpViewDev *__restrict__ vi
     const int kc = min(max(nv - k0, 0), GROUND);   // this group's views in the round
     const int kcmax = min(GROUND, nvmax - k0);     // warp-uniform loop bound
     __syncwarp();
-    dp_setup_views<GL, DpViewSetupG>(views, n_views, vis + k0, kc, kcmax, s, f, recs, lane, false);
+    dp_setup_views<GL, DpViewSetupG>(views, n_views, vis + k0, kc, kcmax, s, f, recs, lane);
     __syncwarp();
     unsigned my1 = 0, my2 = 0;
     double mynum = 0.0;
@@ -550,12 +551,13 @@ template <typename C>
 __device__ __forceinline__ double dp_objective_g(const DpViewDev *__restrict__ views, int n_views,
                                                  int ref, const int32_t *vis, int nv, int s, int npx,
                                                  const double n[3], const double p[3],
+                                                 const double pc[3],
                                                  DpViewSetupG *recs, const double2 *txy,
                                                  uint8_t *gs, uint32_t *tile, int lane,
                                                  const DpGroupLane &L) {
   double sum = 0.0;
   dp_eval_views_g<C, false>(
-      views, n_views, ref, true, vis, nv, s, npx, n, p, recs, txy, gs, tile, lane, L, nullptr, nullptr,
+      views, n_views, ref, true, vis, nv, s, npx, n, p, pc, recs, txy, gs, tile, lane, L, nullptr, nullptr,
       [&](int k0, int kc, int kcmax, double score) {
         // std::accumulate of (1 - NCC) in view order (optimization_opencv.cpp:24, 34)
         const double term = xsub(1.0, score);
@@ -620,6 +622,9 @@ dp_score_group_kernel(DpScoreArgs a, const int32_t *__restrict__ order) {
   const bool ref_ok = ref >= 0 && ref < a.p.n_views;
   double n[3] = {(double)a.p.nrm[3 * i], (double)a.p.nrm[3 * i + 1], (double)a.p.nrm[3 * i + 2]};
   double p[3] = {(double)a.p.pos[3 * i], (double)a.p.pos[3 * i + 1], (double)a.p.pos[3 * i + 2]};
+  const double pc[3] = {p[0], p[1], p[2]};
+  if (a.trial_nrm) { n[0] = a.trial_nrm[3 * i]; n[1] = a.trial_nrm[3 * i + 1]; n[2] = a.trial_nrm[3 * i + 2]; }
+  if (a.trial_pos) { p[0] = a.trial_pos[3 * i]; p[1] = a.trial_pos[3 * i + 1]; p[2] = a.trial_pos[3 * i + 2]; }
   int32_t *vis = a.p.vis + (size_t)i * a.p.vstride;
   float *ncc = a.ncc ? a.ncc + (size_t)i * a.p.vstride : nullptr;
   uint8_t *tex = WRITE_TEX ? a.tex + (size_t)i * a.p.vstride * npx * 3 : nullptr;
@@ -628,7 +633,7 @@ dp_score_group_kernel(DpScoreArgs a, const int32_t *__restrict__ order) {
   const double thr = a.thr;
   const unsigned lt = (1u << L.sub) - 1u;
   dp_eval_views_g<C, WRITE_TEX>(
-      a.p.views, a.p.n_views, ref, ref_ok, vis, nv, s, npx, n, p,
+      a.p.views, a.p.n_views, ref, ref_ok, vis, nv, s, npx, n, p, pc,
       sh.recs[warp][grp], sh.txy + L.sub, &sh.gray[warp][0][lane], sh.group_tile(warp, grp), lane, L,
       tex, valid, [&](int k0, int kc, int kcmax, double score) {
         const int k = k0 + L.sub;
@@ -734,15 +739,15 @@ __global__ void __launch_bounds__(DP_GWARPS * 32, DP_GMINCTA) dp_refine_group_ke
     if (!__any_sync(DP_FULL, have)) break;
     // ---- 2. one objective evaluation per group, in lockstep ---------------------------------
     double n[3], p[3];
+    const double p0[3] = {S.p0[0], S.p0[1], S.p0[2]};  // GetPosition(): the corner centre
     {
       const double c3[3] = {S.c3[0], S.c3[1], S.c3[2]};
       const double n0[3] = {S.n0[0], S.n0[1], S.n0[2]};
-      const double p0[3] = {S.p0[0], S.p0[1], S.p0[2]};
       dp_unparametrize_g(c3, n0, p0, S.pt[0], S.pt[1], S.pt[2], n, p, L, DP_FULL);
     }
     const int nv_eval = (have && nv >= 2 && ref_ok) ? nv : 0;
     const double fobj = dp_objective_g<C>(a.p.views, a.p.n_views, ref_ok ? ref : 0, vis, nv_eval, s,
-                                           npx, n, p, recs, txy, &sh.gray[warp][0][lane],
+                                           npx, n, p, p0, recs, txy, &sh.gray[warp][0][lane],
                                            sh.group_tile(warp, grp), lane, L);
     const double fval = nv_eval ? fobj : 2.0;  // scores.size() == 0 (optimization_opencv.cpp:30-32)
     // ---- 3. Nelder-Mead bookkeeping of each group (diverges by solver state, short) ---------
@@ -752,7 +757,6 @@ __global__ void __launch_bounds__(DP_GWARPS * 32, DP_GMINCTA) dp_refine_group_ke
         // SetNormal / SetPosition store fp32 (patch.h:38-53)
         const double c3[3] = {S.c3[0], S.c3[1], S.c3[2]};
         const double n0[3] = {S.n0[0], S.n0[1], S.n0[2]};
-        const double p0[3] = {S.p0[0], S.p0[1], S.p0[2]};
         double nb[3], pb[3];
         dp_unparametrize_g(c3, n0, p0, S.pt[0], S.pt[1], S.pt[2], nb, pb, L, L.mask);
         if (L.sub < 3) {

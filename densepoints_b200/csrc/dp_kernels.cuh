@@ -39,6 +39,9 @@ struct DpScoreArgs {
   float *ncc;      // n*vstride or null
   uint8_t *tex;    // n*vstride*s*s*3 or null
   uint8_t *valid;  // n*vstride or null
+  // GetProjectedTextures(normal, position, textures): optional trial arguments, n*3 fp64 each
+  // (null = the patch's own); the stored pos stays the corner centre (patch.cpp:119-123)
+  const double *trial_nrm, *trial_pos;
   // filter epilogue
   double thr;
   int min_visible;
@@ -47,40 +50,29 @@ struct DpScoreArgs {
 
 // How the texel pass gets its source pixels is a per-kernel choice, measured on B200
 // (profiles/r01_summary.md):
-//  * score / filter kernel (TMA = true): every patch is visited once, nothing is reused, so
-//    the ROI is staged in shared memory -- by TMA when the footprint fits one 16x16 box (up
-//    to 4 texel passes, s <= 11: two 1 KB buffers per warp, the next view's box in flight
-//    while the current one is computed), else by the warp itself into one buffer of kTilePx
-//    pixels (~4x the texel count, for oblique / zoomed views) or, beyond that, not at all.
-//  * refine kernel (TMA = false): consecutive Nelder-Mead evaluations of a patch read almost
+//  * score / filter kernel (STAGE = true): every patch is visited once, nothing is reused, so
+//    the warp stages the ROI into one shared-memory buffer of kTilePx pixels (~4x the texel
+//    count, for oblique / zoomed views) or, beyond that, not at all.
+//  * refine kernel (STAGE = false): consecutive Nelder-Mead evaluations of a patch read almost
 //    the same pixels, 97 % of the loads hit L1, and staging them again for every evaluation
 //    costs more than it saves: the taps are gathered straight from global memory (+16 % over
-//    staging; TMA staging -3 %, cp.async double buffering -1 %, tld4 texture gather +2 %).
-template <int NPASS, bool TMA>
+//    staging; cp.async double buffering -1 %, tld4 texture gather +2 %).
+// (Round 1 also staged footprints that fit a 16x16 box by TMA -- cp.async.bulk.tensor.2d from a
+// per-view tensor map, mbarrier, two buffers.  Measured and retired: the TMA warp-per-patch
+// score kernel reached 1.74 G evals/s against 2.62 for the cp.async group kernel that now
+// serves those cell sizes, and TMA staging in the refine kernel lost 3 %; the probe that found
+// the 16-byte alignment rule of the tile coordinate is kept in tools/probe/.)
+template <int NPASS, bool STAGE>
 struct DpTileCfg {
-  static constexpr bool kTma = TMA && NPASS <= 4;
-  static constexpr bool kDirect = !TMA;
-  static constexpr int kTilePx =
-      kDirect ? 1 : (kTma ? DP_TMA_BOX * DP_TMA_BOX : (128 * NPASS < 768 ? 128 * NPASS : 768));
-  static constexpr int kBufs = kTma ? 2 : 1;
+  static constexpr bool kDirect = !STAGE;
+  static constexpr int kTilePx = kDirect ? 1 : (128 * NPASS < 768 ? 128 * NPASS : 768);
 };
 
 // Per-warp shared memory of the score / refine kernels.
-template <int NPASS, bool TMA>
+template <int NPASS, bool STAGE>
 struct __align__(128) DpWarpShared {
-  uint32_t tile[DpTileCfg<NPASS, TMA>::kBufs][DpTileCfg<NPASS, TMA>::kTilePx];
+  uint32_t tile[DpTileCfg<NPASS, STAGE>::kTilePx];
   DpViewSetup recs[DP_ROUND];
-  uint64_t bar[2];
-  __device__ __forceinline__ void init(int lane) {
-    if (DpTileCfg<NPASS, TMA>::kTma) {
-      if (lane == 0) {
-        dp_mbar_init(&bar[0], 1);
-        dp_mbar_init(&bar[1], 1);
-        dp_mbar_init_fence();
-      }
-      __syncwarp();
-    }
-  }
 };
 
 // Evaluate all visible views of one patch at (n, p), DP_ROUND views per round:
@@ -90,18 +82,18 @@ struct __align__(128) DpWarpShared {
 // After each round sink(k0, kc, score) is called with lane l holding the score of view
 // k0 + l (l < kc; -1 when either texture is empty, error_measurements.cpp:38-40; the entry
 // of view 0 is meaningless).
-template <int NPASS, bool WRITE_TEX, bool TMA, typename Sink>
+template <int NPASS, bool WRITE_TEX, bool STAGE, typename Sink>
 __device__ __forceinline__ void dp_eval_views(const DpViewDev *__restrict__ views, int n_views,
                                               int ref, const int32_t *vis, int nv, int s, int npx,
                                               const double n[3], const double p[3],
-                                              const DpTexels<NPASS> &tx, DpWarpShared<NPASS, TMA> &ws,
-                                              unsigned &phase, int lane, uint8_t *tex_base,
+                                              const double pc[3],
+                                              const DpTexels<NPASS> &tx, DpWarpShared<NPASS, STAGE> &ws,
+                                              int lane, uint8_t *tex_base,
                                               uint8_t *valid_base, Sink sink) {
-  constexpr bool kTma = DpTileCfg<NPASS, TMA>::kTma;
   DpViewSetup *recs = ws.recs;
   DpFrame f;
   if (ref >= 0 && ref < n_views)
-    dp_make_frame(views + ref, s, n, p, f);
+    dp_make_frame(views + ref, s, n, p, pc, f);
   else
     f.ok = false;
   const double scale = 1.0 / (double)npx;  // cv::meanStdDev: mean = sum * (1/N)
@@ -112,10 +104,8 @@ __device__ __forceinline__ void dp_eval_views(const DpViewDev *__restrict__ view
   for (int k0 = 0; k0 < nv; k0 += DP_ROUND) {
     const int kc = min(DP_ROUND, nv - k0);
     __syncwarp();
-    dp_setup_views<32>(views, n_views, vis + k0, kc, kc, s, f, recs, lane, kTma);
+    dp_setup_views<32>(views, n_views, vis + k0, kc, kc, s, f, recs, lane);
     __syncwarp();
-    if (kTma && lane == 0 && recs[0].ok && recs[0].tmap != nullptr)  // first box of the round
-      dp_tma_load_tile(ws.tile[0], recs[0].tmap, recs[0].tlx, recs[0].tly, &ws.bar[0]);
     unsigned my1 = 0, my2 = 0;
     double mynum = 0.0;
     int myok = 0;
@@ -123,31 +113,20 @@ __device__ __forceinline__ void dp_eval_views(const DpViewDev *__restrict__ view
     for (int l = 0; l < kc; ++l) {
       const DpViewSetup &R = recs[l];
       const bool ok = R.ok != 0;  // warp-uniform
-      const int b = kTma ? (l & 1) : 0;
-      if (kTma && lane == 0 && l + 1 < kc) {  // next view's box goes into the other buffer
-        const DpViewSetup &Rn = recs[l + 1];
-        if (Rn.ok && Rn.tmap != nullptr)
-          dp_tma_load_tile(ws.tile[b ^ 1], Rn.tmap, Rn.tlx, Rn.tly, &ws.bar[b ^ 1]);
-      }
       unsigned s1 = 0, s2 = 0;
       double num = 0.0;
       if (ok) {
         bool staged = false;
-        if (kTma && R.tmap != nullptr) {
-          dp_mbar_wait(&ws.bar[b], (phase >> b) & 1u);
-          phase ^= 1u << b;
-          staged = true;
-        } else if (!DpTileCfg<NPASS, TMA>::kDirect) {
-          staged = dp_stage_roi<(NPASS < 4 ? NPASS : 4)>(R, ws.tile[b],
-                                                         DpTileCfg<NPASS, TMA>::kTilePx, lane);
-        }
+        if (!DpTileCfg<NPASS, STAGE>::kDirect)
+          staged = dp_stage_roi<(NPASS < 4 ? NPASS : 4)>(R, ws.tile, DpTileCfg<NPASS, STAGE>::kTilePx,
+                                                         lane);
         int g[NPASS];
         uint8_t *tex_out = WRITE_TEX ? tex_base + (size_t)(k0 + l) * npx * 3 : nullptr;
         // two instantiations, so neither texel loop carries the other's addressing
         if (staged)
-          dp_view_texture<NPASS, WRITE_TEX, true>(R, npx, tx, ws.tile[b], lane, g, tex_out);
+          dp_view_texture<NPASS, WRITE_TEX, true>(R, npx, tx, ws.tile, lane, g, tex_out);
         else
-          dp_view_texture<NPASS, WRITE_TEX, false>(R, npx, tx, ws.tile[b], lane, g, tex_out);
+          dp_view_texture<NPASS, WRITE_TEX, false>(R, npx, tx, ws.tile, lane, g, tex_out);
         dp_moments<NPASS>(g, s1, s2);
         if (k0 + l == 0) {
           a1 = s1;
@@ -184,8 +163,6 @@ __global__ void __launch_bounds__(DP_WARPS * 32, dp_score_min_ctas(NPASS)) dp_sc
   const long long i = (long long)blockIdx.x * DP_WARPS + warp;
   if (i >= a.p.n) return;
   DpWarpShared<NPASS, true> &ws = wsh[warp];
-  ws.init(lane);
-  unsigned phase = 0;
   const int s = a.p.s, npx = s * s;
   DpTexels<NPASS> tx;
   tx.init(s, lane);
@@ -193,6 +170,9 @@ __global__ void __launch_bounds__(DP_WARPS * 32, dp_score_min_ctas(NPASS)) dp_sc
   const int ref = a.p.ref[i];
   double n[3] = {(double)a.p.nrm[3 * i], (double)a.p.nrm[3 * i + 1], (double)a.p.nrm[3 * i + 2]};
   double p[3] = {(double)a.p.pos[3 * i], (double)a.p.pos[3 * i + 1], (double)a.p.pos[3 * i + 2]};
+  const double pc[3] = {p[0], p[1], p[2]};
+  if (a.trial_nrm) { n[0] = a.trial_nrm[3 * i]; n[1] = a.trial_nrm[3 * i + 1]; n[2] = a.trial_nrm[3 * i + 2]; }
+  if (a.trial_pos) { p[0] = a.trial_pos[3 * i]; p[1] = a.trial_pos[3 * i + 1]; p[2] = a.trial_pos[3 * i + 2]; }
   int32_t *vis = a.p.vis + (size_t)i * a.p.vstride;
   float *ncc = a.ncc ? a.ncc + (size_t)i * a.p.vstride : nullptr;
   uint8_t *tex = WRITE_TEX ? a.tex + (size_t)i * a.p.vstride * npx * 3 : nullptr;
@@ -207,7 +187,7 @@ __global__ void __launch_bounds__(DP_WARPS * 32, dp_score_min_ctas(NPASS)) dp_sc
   const double thr = a.thr;
   const unsigned lt = (1u << lane) - 1u;
   dp_eval_views<NPASS, WRITE_TEX, true>(
-      a.p.views, a.p.n_views, ref, vis, nv, s, npx, n, p, tx, ws, phase, lane, tex, valid,
+      a.p.views, a.p.n_views, ref, vis, nv, s, npx, n, p, pc, tx, ws, lane, tex, valid,
       [&](int k0, int kc, double score) {
         const int k = k0 + lane;
         const bool mine = lane < kc && k >= 1;
@@ -391,8 +371,6 @@ __global__ void __launch_bounds__(DP_RWARPS * 32, dp_refine_min_ctas(NPASS)) dp_
   DpTexels<NPASS> tx;
   tx.init(s, lane);
   DpWarpShared<NPASS, false> &ws = wsh[warp];
-  ws.init(lane);
-  unsigned phase = 0;
   DpNelderMead &S = nm[warp];
   enum { ST_INIT, ST_REFLECT, ST_EXPAND, ST_CONTRACT, ST_SHRINK, ST_DONE };
   for (;;) {
@@ -432,10 +410,10 @@ __global__ void __launch_bounds__(DP_RWARPS * 32, dp_refine_min_ctas(NPASS)) dp_
     for (;;) {
       // UnparametrizePatch at the point to evaluate (or, in ST_DONE, at the best vertex)
       double n[3], p[3];
+      const double p0[3] = {S.p0[0], S.p0[1], S.p0[2]};  // GetPosition(): the corner centre
       {
         const double c3[3] = {S.c3[0], S.c3[1], S.c3[2]};
         const double n0[3] = {S.n0[0], S.n0[1], S.n0[2]};
-        const double p0[3] = {S.p0[0], S.p0[1], S.p0[2]};
         dp_unparametrize(c3, n0, p0, S.pt[0], S.pt[1], S.pt[2], n, p);
       }
       if (state == ST_DONE) {
@@ -457,7 +435,7 @@ __global__ void __launch_bounds__(DP_RWARPS * 32, dp_refine_min_ctas(NPASS)) dp_
       if (nv >= 2 && ref_ok) {
         double sum = 0.0;
         dp_eval_views<NPASS, false, false>(
-            a.p.views, a.p.n_views, ref, vis, nv, s, npx, n, p, tx, ws, phase, lane, nullptr,
+            a.p.views, a.p.n_views, ref, vis, nv, s, npx, n, p, p0, tx, ws, lane, nullptr,
             nullptr, [&](int k0, int kc, double score) {
               // std::accumulate of (1 - NCC) in view order (optimization_opencv.cpp:24, 34)
               const double term = xsub(1.0, score);

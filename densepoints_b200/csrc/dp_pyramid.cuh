@@ -46,7 +46,7 @@ dp_pyrdown_kernel(const uint32_t *__restrict__ src, int sw, int sh, int spitch,
 
 extern "C" int dp_build_pyramid(dp_context *ctx, int n_levels) {
   if (!ctx || n_levels < 1 || n_levels > 16) return dp_fail(ctx, DP_ERR_INVALID_ARG, "n_levels");
-  cudaSetDevice(ctx->device);
+  DpDeviceGuard guard__(ctx->device);
   cudaStream_t st = ctx->stream;
   for (auto &v : ctx->views) {
     if (!v.set) return dp_fail(ctx, DP_ERR_STATE, "a view was not uploaded");
@@ -61,13 +61,12 @@ extern "C" int dp_build_pyramid(dp_context *ctx, int n_levels) {
       d.height = (s.height + 1) / 2;
       d.pitch_px = (d.width + 31) & ~31;
       DP_CUDA(ctx, cudaMalloc(&d.img, (size_t)d.pitch_px * (d.height + 1) * sizeof(uint32_t)));  // + spare row
+      v.levels.push_back(d);  // owned by the view from here on (no leak on a later failure)
       DP_CUDA(ctx, cudaMemsetAsync(d.img + (size_t)d.pitch_px * d.height, 0, (size_t)d.pitch_px * 4, st));
       dim3 grid((d.pitch_px + 255) / 256, d.height);
       dp_pyrdown_kernel<<<grid, 256, 0, st>>>(s.img, s.width, s.height, s.pitch_px, d.img, d.width,
                                               d.height, d.pitch_px);
       ++ctx->launches;
-      dp_encode_tmap(d);
-      v.levels.push_back(d);
     }
   }
   DP_CUDA(ctx, cudaGetLastError());
@@ -103,7 +102,7 @@ extern "C" int dp_download_level(dp_context *ctx, int view_id, int level, uint8_
   if (!bgr) return DP_OK;
   const size_t bytes = (size_t)l.width * l.height * 3;
   if (capacity < bytes) return dp_fail(ctx, DP_ERR_INVALID_ARG, "capacity");
-  cudaSetDevice(ctx->device);
+  DpDeviceGuard guard__(ctx->device);
   DP_CUDA(ctx, ctx->s_img.ensure(bytes));
   dim3 grid((l.width + 255) / 256, l.height);
   dp_unpack_bgrx_kernel<<<grid, 256, 0, ctx->stream>>>(l.img, l.pitch_px, l.width, l.height,

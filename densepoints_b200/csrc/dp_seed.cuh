@@ -43,7 +43,7 @@ extern "C" int dp_create_patches(dp_context *ctx, const double *points, int n, d
     return dp_fail(ctx, DP_ERR_INVALID_ARG, "dp_create_patches: output capacity");
   out->n = n;
   if (n == 0) return DP_OK;
-  cudaSetDevice(ctx->device);
+  DpDeviceGuard guard__(ctx->device);
   int rc = dp_sync_views(ctx);
   if (rc != DP_OK) return rc;
   cudaStream_t st = ctx->stream;
@@ -83,7 +83,7 @@ extern "C" int dp_create_patches(dp_context *ctx, const double *points, int n, d
 extern "C" int dp_export_ply(dp_context *ctx, const char *path) {
   if (!ctx || !path) return dp_fail(ctx, DP_ERR_INVALID_ARG, "dp_export_ply");
   if (!ctx->org.ready) return dp_fail(ctx, DP_ERR_STATE, "call dp_organizer_reset first");
-  cudaSetDevice(ctx->device);
+  DpDeviceGuard guard__(ctx->device);
   const DpOrganizer &o = ctx->org;
   const size_t n = (size_t)o.n;
   std::vector<float> pos(n * 3), nrm(n * 3);

@@ -7,8 +7,9 @@ the work of a level happens behind the C ABI:
     dp_expand_level_local   refine + visibility + filter of the candidates this rank owns,
                             survivors written as records into the send buffer
     all_gather              counts, then the (padded) record buffers
-    dp_expand_level_commit  every rank replays TryInsert over all records in sequence order
-                            -> identical grids and patch stores on every rank
+    dp_expand_level_commit_gathered
+                            every rank compacts the gathered segments on the device and replays
+                            TryInsert over all records -> identical grids and stores everywhere
 """
 from __future__ import annotations
 
@@ -54,69 +55,136 @@ def share_images(images, rank: int, world: int, device=None):
     return images
 
 
+def assign_views(weights, world: int) -> np.ndarray:
+    """rank_of_view for ONE level from the frontier's work per reference view
+    (dp_expand_frontier_weights): longest-processing-time-first -- views by descending weight
+    (ties: ascending view id), each to the least loaded rank so far (ties: lowest rank).  Every
+    rank computes the same table from the replicated store, so no exchange is needed.  Patches
+    still shard by reference image (children inherit it, reference expand.cpp:126); only which
+    rank serves a view may change from level to level, which costs nothing because views, grids
+    and store are replicated."""
+    w = np.asarray(weights, dtype=np.int64)
+    rov = np.zeros(len(w), np.int32)
+    if world <= 1:
+        return rov
+    load = np.zeros(world, np.int64)
+    for v in sorted(range(len(w)), key=lambda i: (-int(w[i]), i)):
+        r = int(np.argmin(load))
+        rov[v] = r
+        load[r] += int(w[v])
+    return rov
+
+
 class CudaLevelBackend:
-    """The three per-level steps on a dp_context (device records = torch int32 tensors)."""
+    """The per-level steps on a dp_context (device records = torch int32 tensors)."""
 
     def __init__(self, ctx, device):
         self.ctx = ctx
         self.device = device
         self.words = ctx.record_bytes() // 4
+        self._buf = None
 
     def frontier(self):
         return self.ctx.expand_frontier()
 
-    def local(self, cell_size, rank, world, rank_of_view, max_records):
-        buf = torch.empty((max(max_records, 1), self.words), dtype=torch.int32, device=self.device)
-        n = self.ctx.expand_level_local(cell_size, rank, world, rank_of_view, buf.data_ptr(),
-                                        max_records,
-                                        stream=torch.cuda.current_stream().cuda_stream)
-        return buf, n
+    def frontier_weights(self):
+        return self.ctx.expand_frontier_weights()
 
-    def commit(self, records, n_records):
-        return self.ctx.expand_level_commit(records.data_ptr() if n_records else 0, n_records,
-                                            stream=torch.cuda.current_stream().cuda_stream)
+    def _stream(self):
+        return torch.cuda.current_stream().cuda_stream
+
+    def local(self, cell_size, rank, world, rank_of_view, max_records):
+        if self._buf is None or self._buf.shape[0] < max(max_records, 1):
+            self._buf = torch.empty((max(max_records, 1), self.words), dtype=torch.int32,
+                                    device=self.device)
+        n = self.ctx.expand_level_local(cell_size, rank, world, rank_of_view, self._buf.data_ptr(),
+                                        max_records, stream=self._stream())
+        return self._buf, n
+
+    def last_candidates(self):
+        return self.ctx.expand_last_candidates()
+
+    def commit_gathered(self, recv, world, capacity, counts):
+        return self.ctx.expand_level_commit_gathered(recv.data_ptr(), world, capacity, counts,
+                                                     stream=self._stream())
+
+    def mark(self):
+        """A timing mark on the stream the level's work is launched on."""
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    @staticmethod
+    def elapsed_ms(a, b):
+        b.synchronize()
+        return a.elapsed_time(b)
 
 
 def gather_records(buf: torch.Tensor, n_local: int, world: int):
-    """allgather of ragged record lists: counts first, then buffers padded to the level's
-    maximum; returns (records [total, words] in rank order, total)."""
+    """allgather of ragged record lists: the counts (one tiny collective, read on the host
+    because the commit sizes its launches from them), then the buffers padded to the level's
+    maximum.  Returns (gathered [world * capacity, words], counts list, capacity); the ragged
+    segments are compacted on the device by dp_expand_level_commit_gathered."""
     if world <= 1:
-        return buf[:n_local], n_local
+        return buf, [n_local], max(int(buf.shape[0]), 1)
     cnt = torch.tensor([n_local], dtype=torch.int64, device=buf.device)
     counts = torch.empty(world, dtype=torch.int64, device=buf.device)
     dist.all_gather_into_tensor(counts, cnt)
     counts = counts.cpu().tolist()
-    mx = max(counts)
-    if mx == 0:
-        return buf[:0], 0
-    send = buf[:mx] if buf.shape[0] >= mx else torch.cat(
-        [buf, buf.new_zeros((mx - buf.shape[0], buf.shape[1]))])
-    send = send.contiguous()
-    recv = torch.empty((world * mx, buf.shape[1]), dtype=buf.dtype, device=buf.device)
-    dist.all_gather_into_tensor(recv, send)
-    parts = [recv[r * mx: r * mx + c] for r, c in enumerate(counts) if c > 0]
-    out = torch.cat(parts).contiguous() if len(parts) > 1 else parts[0].contiguous()
-    return out, int(sum(counts))
+    cap = max(max(counts), 1)
+    recv = torch.empty((world * cap, buf.shape[1]), dtype=buf.dtype, device=buf.device)
+    send = buf[:cap]                                    # rows beyond n_local are padding
+    if send.shape[0] < cap:                             # (a backend with an exact-size buffer)
+        send = torch.cat([send, send.new_zeros((cap - send.shape[0], send.shape[1]))])
+    dist.all_gather_into_tensor(recv, send.contiguous())
+    return recv, counts, cap
 
 
 def expand_distributed(backend, cell_size: int, max_levels: int, rank: int, world: int,
-                       rank_of_view) -> dict:
+                       rank_of_view=None, timings=None) -> dict:
     """Expand::ExpandPatches (reference expand.cpp:34-101) across `world` ranks.  The
-    organizer must hold the same seeds on every rank (dp_organizer_insert on each)."""
+    organizer must hold the same seeds on every rank (dp_organizer_insert on each).
+    rank_of_view: a fixed ownership table (partition_views), or None = re-balanced every level
+    from the frontier's work per reference view (assign_views).  timings (optional dict): per
+    level lists local_ms / allgather_ms / commit_ms and the record counts, when the backend can
+    time its stream."""
     stats = dict(levels=0, pops=0, passed=0, inserted=0, local_records=0)
     level = 0
+    can_time = timings is not None and hasattr(backend, "mark")
+    if timings is not None:
+        for k in ("local_ms", "allgather_ms", "commit_ms", "frontier", "records", "local_records",
+                  "local_candidates"):
+            timings.setdefault(k, [])
     while max_levels < 0 or level < max_levels:
         fb, fe = backend.frontier()
         nf = fe - fb
         if nf <= 0:
             break
-        buf, n_local = backend.local(cell_size, rank, world, rank_of_view, 4 * nf)
-        records, total = gather_records(buf, n_local, world)
-        inserted = backend.commit(records, total)
+        rov = rank_of_view
+        if rov is None and world > 1:
+            rov = assign_views(backend.frontier_weights(), world)
+        t0 = backend.mark() if can_time else None
+        buf, n_local = backend.local(cell_size, rank, world, rov, 4 * nf)
+        t1 = backend.mark() if can_time else None
+        recv, counts, cap = gather_records(buf, n_local, world)
+        t2 = backend.mark() if can_time else None
+        inserted = backend.commit_gathered(recv, world, cap, counts)
+        t3 = backend.mark() if can_time else None
+        total = int(sum(counts))
         stats["levels"] += 1
         stats["pops"] += nf
         stats["passed"] += total
         stats["inserted"] += inserted
         stats["local_records"] += n_local
+        if timings is not None:
+            timings["frontier"].append(int(nf))
+            timings["records"].append(total)
+            timings["local_records"].append(int(n_local))
+            if hasattr(backend, "last_candidates"):
+                timings["local_candidates"].append(int(backend.last_candidates()))
+            if can_time:
+                timings["local_ms"].append(backend.elapsed_ms(t0, t1))
+                timings["allgather_ms"].append(backend.elapsed_ms(t1, t2))
+                timings["commit_ms"].append(backend.elapsed_ms(t2, t3))
         level += 1
     return stats

@@ -120,10 +120,12 @@ def _render(P_list, centers, Rs, f, cx, cy, width, height, surface, param, tex, 
     return images
 
 
-def _render_torch(centers, Rs, f, cx, cy, width, height, surface, param, tex, device):
+def _render_torch(centers, Rs, f, cx, cy, width, height, surface, param, tex, device,
+                  only_views=None):
     """_render on a torch device (fp64): for the large benchmark scenes only (64 x 1920x1080 takes
     minutes in numpy).  Test-data plumbing, not the product; pixel values may differ from the
-    numpy renderer in the last bit of sin(), so golden vectors always use _render."""
+    numpy renderer in the last bit of sin(), so golden vectors always use _render.
+    only_views: as in _render (the other views stay black)."""
     import torch
     dev = torch.device(device)
     t64 = lambda a: torch.as_tensor(np.asarray(a, np.float64), device=dev)
@@ -134,7 +136,10 @@ def _render_torch(centers, Rs, f, cx, cy, width, height, surface, param, tex, de
     kb, pb = t64(tex.kb), t64(tex.pb)
     kc = [(t64(k), t64(p)) for k, p in tex.kc]
     images = []
-    for C0, R in zip(centers, Rs):
+    for vid, (C0, R) in enumerate(zip(centers, Rs)):
+        if only_views is not None and vid not in only_views:
+            images.append(np.zeros((height, width, 3), np.uint8))
+            continue
         C0t, Rt = t64(C0), t64(R)
         d = pix @ Rt
         if surface == "plane":
@@ -183,8 +188,9 @@ def make_plane_scene(seed=1, n_views=3, width=640, height=480, f=None, distance=
         Ps.append(projection(f, cx, cy, R, c))
     px_world = distance / f
     tex = Texture3D(seed + 1000, (3.0 * px_world, 14.0 * px_world))
-    if device is not None and only_views is None:
-        images = _render_torch(centers, Rs, f, cx, cy, width, height, "plane", extent, tex, device)
+    if device is not None:
+        images = _render_torch(centers, Rs, f, cx, cy, width, height, "plane", extent, tex, device,
+                               only_views=only_views)
     else:
         images = _render(Ps, centers, Rs, f, cx, cy, width, height, "plane", extent, tex,
                          only_views=only_views)

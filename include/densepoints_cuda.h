@@ -105,6 +105,15 @@ int dp_get_view(const dp_context *ctx, int view_id, double xaxis[3], double cent
 int dp_score(dp_context *ctx, const dp_patch_soa *patches, int cell_size, float *ncc,
              uint8_t *tex, uint8_t *valid);
 
+/* ---- Optimization::GetProjectedTextures(normal, position, textures) (optimization.cpp:14-56),
+ * the public two-argument overload the refinement objective calls
+ * (optimization_opencv.cpp:17-21), + the NCC loop: `normal` / `position` (fp64, n*3 each; NULL =
+ * the patch's own) only feed GetProjectedXYAxisAndScale (axes and dx, optimization.cpp:24-26);
+ * the four corners stay centred on the patch's STORED position (patch.cpp:119-123).
+ * Outputs as dp_score. */
+int dp_score_at(dp_context *ctx, const dp_patch_soa *patches, int cell_size, const double *normal,
+                const double *position, float *ncc, uint8_t *tex, uint8_t *valid);
+
 /* ---- filter: Optimization::FilterByErrorMeasurement (optimization.cpp:98-132)
  * for every patch = body of Seed::FilterPatches (seed.cpp:110-126).
  * nvis/vis are edited in place exactly as the reference erases entries
@@ -142,7 +151,10 @@ int dp_color(dp_context *ctx, dp_patch_soa *patches);
  * Order is the reference's single-thread FIFO order. */
 int dp_organizer_reset(dp_context *ctx); /* AllocateViews, patch_organizer.cpp:32-40 */
 /* SetSeeds (patch_organizer.cpp:70-75): TryInsert each patch in order;
- * accepted (optional) [n] = 1 where TryInsert returned non-null. */
+ * accepted (optional) [n] = 1 where TryInsert returned non-null.  The store keeps a visible
+ * set as a bit mask over the views, so the ids of every patch must be valid and strictly
+ * ascending -- the order Patch::InitRelatedImages produces (patch.cpp:29-47) and
+ * FilterByErrorMeasurement keeps; anything else is DP_ERR_INVALID_ARG. */
 int dp_organizer_insert(dp_context *ctx, const dp_patch_soa *patches, uint8_t *accepted);
 int64_t dp_organizer_size(const dp_context *ctx);
 /* copies the store out; out->n / out->vstride give the capacity of the arrays */
@@ -150,6 +162,8 @@ int dp_organizer_export(dp_context *ctx, dp_patch_soa *out);
 /* occupancy counts of one view's grid, row-major gh x gw (capacity bytes) */
 int dp_organizer_grid(dp_context *ctx, int view_id, uint8_t *out, size_t capacity, int *gw,
                       int *gh);
+/* all grids concatenated in view order; out == NULL only reports *n_cells */
+int dp_organizer_grids(dp_context *ctx, uint8_t *out, size_t capacity, int64_t *n_cells);
 /* Expand::ExpandPatches (expand.cpp:34-101).  max_levels < 0: until the queue is
  * empty (reference behaviour).  stats (optional) [4]: pops, candidates refined,
  * candidates that passed the filter, patches inserted. */
@@ -166,15 +180,31 @@ int dp_expand(dp_context *ctx, int cell_size, int max_levels, int64_t *stats);
  *  2. (caller) allgather counts + records.
  *  3. dp_expand_level_commit : every rank replays TryInsert over all gathered records in
  *     sequence order -> identical grids and stores on every rank. */
+/* A record is 32 bytes (seq, ref | nvis << 16, pos, nrm as fp32 bits) + the visible set as a
+ * bit mask of ceil(n_views / 32) words: 40 bytes at 64 views, 64 bytes at 256 views. */
 size_t dp_record_bytes(const dp_context *ctx);
 int dp_expand_frontier(dp_context *ctx, int64_t *begin, int64_t *end);
+/* weights [n_views] (host): per reference view, the sum of the visible-view counts of the
+ * frontier parents that will expand = the work of owning that view in this level (used to
+ * balance rank_of_view level by level; every rank computes the same numbers). */
+int dp_expand_frontier_weights(dp_context *ctx, int64_t *weights);
 int dp_expand_level_local(dp_context *ctx, int cell_size, int rank, int world,
                           const int32_t *rank_of_view, void *records_dev, int64_t max_records,
                           int64_t *n_records, void *stream);
+/* candidates this rank refined in its last dp_expand_level_local call (bookkeeping) */
+int64_t dp_expand_last_candidates(const dp_context *ctx);
 int dp_expand_level_commit(dp_context *ctx, const void *records_dev, int64_t n_records,
                            int64_t *n_inserted, void *stream);
+/* step 3 straight on the output of an allgather of padded buffers: `world` segments of
+ * segment_capacity records, the first counts[r] (host array) of segment r valid. */
+int dp_expand_level_commit_gathered(dp_context *ctx, const void *gathered_dev, int world,
+                                    int64_t segment_capacity, const int64_t *counts,
+                                    int64_t *n_inserted, void *stream);
 
-/* ---- device-pointer layer (async on `stream`; all pointers are device memory) */
+/* ---- device-pointer layer (async on `stream`; all pointers are device memory).
+ * The calls of one context share internal scratch (work counter, order table, expansion
+ * buffers); calls issued on different streams are chained with events inside the library, so
+ * they run one after the other, never concurrently.  Use one context per stream for overlap. */
 typedef struct dp_patch_dev {
   int32_t n, vstride;
   float *pos, *nrm;
@@ -183,6 +213,8 @@ typedef struct dp_patch_dev {
 } dp_patch_dev;
 int dp_score_dev(dp_context *ctx, const dp_patch_dev *p, int cell_size, float *ncc, uint8_t *tex,
                  uint8_t *valid, void *stream);
+int dp_score_at_dev(dp_context *ctx, const dp_patch_dev *p, int cell_size, const double *normal,
+                    const double *position, float *ncc, uint8_t *tex, uint8_t *valid, void *stream);
 int dp_filter_dev(dp_context *ctx, dp_patch_dev *p, int cell_size, uint8_t *keep, void *stream);
 int dp_refine_dev(dp_context *ctx, dp_patch_dev *p, int cell_size, const uint8_t *mask,
                   int32_t *evals, double *xbest, void *stream);

@@ -622,10 +622,14 @@ int orc_patch_homography(const orc_view *v, int cell_size, const double pos[3], 
   return 1;
 }
 
-/* Optimization::GetProjectedTextures (optimization.cpp:14-56) */
+/* Optimization::GetProjectedTextures(normal, position, textures) (optimization.cpp:14-56).
+ * `nrm` / `pos` are the ARGUMENTS: they only feed GetProjectedXYAxisAndScale (:24-26), i.e.
+ * the patch axes and dx.  The four corners are built around `centre` = patch_.GetPosition(),
+ * the STORED position (patch.cpp:119-123) -- so while Optimize() evaluates a trial depth, the
+ * quad stays centred on the stored point and the depth only changes its scale. */
 void orc_projected_textures(const orc_view *views, int ref, const int *vis, int nvis,
-                            int cell_size, const double nrm[3], const double pos[3], uint8_t *tex,
-                            uint8_t *valid) {
+                            int cell_size, const double nrm[3], const double pos[3],
+                            const double centre[3], uint8_t *tex, uint8_t *valid) {
   double xa[3], ya[3], dx;
   orc_axes_scale(&views[ref], nrm, pos, xa, ya, &dx);
   int s = cell_size;
@@ -645,10 +649,10 @@ void orc_projected_textures(const orc_view *views, int ref, const int *vis, int 
     int roi[4];
     int ok;
     if (g_homography_mode == 0) {
-      ok = orc_patch_homography(v, cell_size, pos, ax, ay, H, roi);
+      ok = orc_patch_homography(v, cell_size, centre, ax, ay, H, roi);
     } else {
       float pts[8];
-      ok = orc_patch_quad(v, pos, ax, ay, pts, roi);
+      ok = orc_patch_quad(v, centre, ax, ay, pts, roi);
       if (ok > 0 && roi[2] > 0 && roi[3] > 0) ok = orc_cell_to_quad(pts, s, M) ? 1 : -1;
     }
     if (ok <= 0 || roi[2] <= 0 || roi[3] <= 0) { /* :45-48 */
@@ -674,14 +678,14 @@ static void f2d3(const float a[3], double b[3]) {
   b[2] = a[2];
 }
 
-/* scores of optimization.cpp:104-110 at (nrm, pos) in fp64 */
+/* scores of optimization.cpp:104-110 at (nrm, pos) in fp64, corners around `centre` */
 static void scores_at(const orc_view *views, int ref, const int *vis, int nvis, int cell_size,
-                      const double nrm[3], const double pos[3], double *scores, uint8_t *tex_out,
-                      uint8_t *valid_out) {
+                      const double nrm[3], const double pos[3], const double centre[3],
+                      double *scores, uint8_t *tex_out, uint8_t *valid_out) {
   int s = cell_size, tb = s * s * 3;
   uint8_t *tex = tex_out ? tex_out : (uint8_t *)malloc((size_t)(nvis > 0 ? nvis : 1) * tb);
   uint8_t *valid = valid_out ? valid_out : (uint8_t *)malloc((size_t)(nvis > 0 ? nvis : 1));
-  orc_projected_textures(views, ref, vis, nvis, cell_size, nrm, pos, tex, valid);
+  orc_projected_textures(views, ref, vis, nvis, cell_size, nrm, pos, centre, tex, valid);
   for (int k = 1; k < nvis; ++k)
     scores[k - 1] = orc_ncc_bgr(valid[0] ? tex : NULL, valid[k] ? tex + (size_t)k * tb : NULL,
                                 s * s);
@@ -694,7 +698,7 @@ void orc_scores(const orc_view *views, int ref, const int *vis, int nvis, int ce
   double n[3], p[3];
   f2d3(nrm, n);
   f2d3(pos, p);
-  scores_at(views, ref, vis, nvis, cell_size, n, p, scores, NULL, NULL);
+  scores_at(views, ref, vis, nvis, cell_size, n, p, p, scores, NULL, NULL);
 }
 
 /* Optimization::FilterByErrorMeasurement (optimization.cpp:98-132), including the
@@ -736,13 +740,14 @@ void orc_unparametrize(const orc_view *ref, const float nrm0[3], const float pos
 /* PatchOptimizationOpenCVFunctor::calc (optimization_opencv.cpp:14-39) */
 double orc_objective(const orc_view *views, int ref, const int *vis, int nvis, int cell_size,
                      const float nrm0[3], const float pos0[3], const double x[3]) {
-  double nrm[3], pos[3];
+  double nrm[3], pos[3], centre[3];
   orc_unparametrize(&views[ref], nrm0, pos0, x[0], x[1], x[2], nrm, pos);
+  f2d3(pos0, centre); /* patch_.GetPosition(): untouched until Optimize() returns (:69-70) */
   int nscores = nvis > 0 ? nvis - 1 : 0;
   if (nscores == 0) return 2; /* :30-32 */
   double sc[256];
   double *scores = nscores <= 256 ? sc : (double *)malloc(sizeof(double) * nscores);
-  scores_at(views, ref, vis, nvis, cell_size, nrm, pos, scores, NULL, NULL);
+  scores_at(views, ref, vis, nvis, cell_size, nrm, pos, centre, scores, NULL, NULL);
   double sum = 0.0;
   for (int k = 0; k < nscores; ++k) sum += 1 - scores[k]; /* :24, std::accumulate */
   if (scores != sc) free(scores);
@@ -873,25 +878,39 @@ void orc_create_patches(const orc_view *views, int n_views, int n, const double 
 /* ------------------------------------------------------------------------ */
 /* batched drivers (Seed::FilterPatches / OptimizePatches, seed.cpp:110-144)  */
 
-void orc_score_batch(const orc_view *views, int n, const float *pos, const float *nrm,
-                     const int *ref, const int *nvis, const int *vis, int vstride, int cell_size,
-                     float *ncc, uint8_t *tex, uint8_t *valid) {
+/* GetProjectedTextures(normal, position, textures) + the NCC loop for every patch, at trial
+ * parameters: trial_nrm / trial_pos (fp64, n*3, either may be NULL = the patch's own) are the
+ * arguments of optimization.cpp:14, the stored pos stays the corner centre (patch.cpp:119-123). */
+void orc_score_at_batch(const orc_view *views, int n, const float *pos, const float *nrm,
+                        const int *ref, const int *nvis, const int *vis, int vstride,
+                        int cell_size, const double *trial_nrm, const double *trial_pos,
+                        float *ncc, uint8_t *tex, uint8_t *valid) {
   int tb = cell_size * cell_size * 3;
 #pragma omp parallel for schedule(dynamic, 64)
   for (int i = 0; i < n; ++i) {
     double sc[256];
     int nv = nvis[i];
-    double nn[3], pp[3];
+    double nn[3], pp[3], cc[3];
     f2d3(nrm + 3 * i, nn);
     f2d3(pos + 3 * i, pp);
+    f2d3(pos + 3 * i, cc);
+    if (trial_nrm) memcpy(nn, trial_nrm + 3 * (size_t)i, sizeof(nn));
+    if (trial_pos) memcpy(pp, trial_pos + 3 * (size_t)i, sizeof(pp));
     uint8_t *t = tex ? tex + (size_t)i * vstride * tb : NULL;
     uint8_t *vl = valid ? valid + (size_t)i * vstride : NULL;
     if (vl) memset(vl, 0, vstride);
-    scores_at(views, ref[i], vis + (size_t)i * vstride, nv, cell_size, nn, pp, sc, t, vl);
+    scores_at(views, ref[i], vis + (size_t)i * vstride, nv, cell_size, nn, pp, cc, sc, t, vl);
     ncc[(size_t)i * vstride] = 0.f;
     for (int k = 1; k < vstride; ++k)
       ncc[(size_t)i * vstride + k] = k < nv ? (float)sc[k - 1] : 0.f;
   }
+}
+
+void orc_score_batch(const orc_view *views, int n, const float *pos, const float *nrm,
+                     const int *ref, const int *nvis, const int *vis, int vstride, int cell_size,
+                     float *ncc, uint8_t *tex, uint8_t *valid) {
+  orc_score_at_batch(views, n, pos, nrm, ref, nvis, vis, vstride, cell_size, NULL, NULL, ncc, tex,
+                     valid);
 }
 
 void orc_filter_batch(const orc_view *views, int n, const float *pos, const float *nrm,
@@ -1004,8 +1023,11 @@ const uint8_t *orc_organizer_grid(const orc_organizer *o, int view, int *gw, int
 }
 
 /* PatchOrganizer::TryInsert + PatchGrid::TryInsert (patch_organizer.cpp:42-65, 15-30).
- * (size_t) casts of negative / NaN quotients are UB in the reference; they are
- * defined here as out of bounds. */
+ * static_cast<size_t>(q) truncates toward zero: a quotient in (-1, 0) is cell 0 (defined
+ * behaviour -- a refined seed can project to u or v in (-grid_scale, 0) in a view it kept
+ * from the pre-refinement InitRelatedImages).  q <= -1, NaN and q >= 2^63 are UB in the
+ * reference; they are defined here as out of bounds (x86-64's cvttsd2si gives 2^63 for
+ * them, which fails the bounds test too). */
 long long orc_organizer_try_insert(orc_organizer *o, const float pos[3], const float nrm[3], int ref,
                                    const int *vis, int nvis, int *ncells_out, int *cells_out) {
   double p[3];
@@ -1016,8 +1038,8 @@ long long orc_organizer_try_insert(orc_organizer *o, const float pos[3], const f
     double uv[2];
     orc_project(&o->views[v], p, uv);
     double qr = uv[1] / (double)o->prm.grid_scale, qc = uv[0] / (double)o->prm.grid_scale;
-    if (!(qr >= 0) || !(qc >= 0) || !(qr < 2147483647.0) || !(qc < 2147483647.0)) continue;
-    long long row = (long long)qr, col = (long long)qc;
+    if (!(qr > -1.0) || !(qc > -1.0) || !(qr < 2147483647.0) || !(qc < 2147483647.0)) continue;
+    long long row = (long long)qr, col = (long long)qc; /* truncation toward zero */
     if (col < o->gw[v] && row < o->gh[v]) {
       uint8_t *cell = &o->grid[v][row * o->gw[v] + col];
       if (*cell < o->prm.max_patches_per_cell) {

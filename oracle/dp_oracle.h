@@ -113,11 +113,13 @@ void orc_axes_scale(const orc_view *ref, const double nrm[3], const double pos[3
 /* Patch::ComputePatchToViewHomography (patch.cpp:111-164). roi = x,y,w,h. */
 int orc_patch_homography(const orc_view *v, int cell_size, const double pos[3], const double ax[3],
                          const double ay[3], double H[9], int roi[4]);
-/* Optimization::GetProjectedTextures (optimization.cpp:14-56).
+/* Optimization::GetProjectedTextures(normal, position, textures) (optimization.cpp:14-56).
+ * nrm / pos = the arguments (axes and dx only); centre = patch_.GetPosition(), around which
+ * ComputePatchToViewHomography builds the corners (patch.cpp:119-123).
  * tex: nvis * s*s*3 bytes; valid[k] = 0 for an empty cv::Mat. */
 void orc_projected_textures(const orc_view *views, int ref, const int *vis, int nvis,
-                            int cell_size, const double nrm[3], const double pos[3], uint8_t *tex,
-                            uint8_t *valid);
+                            int cell_size, const double nrm[3], const double pos[3],
+                            const double centre[3], uint8_t *tex, uint8_t *valid);
 /* scores[k-1] = NCCScore(tex0, texk) k=1..nvis-1 (optimization.cpp:104-110). */
 void orc_scores(const orc_view *views, int ref, const int *vis, int nvis, int cell_size,
                 const float nrm[3], const float pos[3], double *scores);
@@ -147,6 +149,12 @@ void orc_score_batch(const orc_view *views, int n, const float *pos, const float
                      const int *ref, const int *nvis, const int *vis, int vstride, int cell_size,
                      float *ncc /* n*vstride, [k] = score of vis[k], k>=1; [0] unused */,
                      uint8_t *tex /* optional n*vstride*s*s*3 */, uint8_t *valid /* optional */);
+/* the same at trial parameters = Optimization::GetProjectedTextures(normal, position, ...)
+ * (optimization.cpp:14-56): trial_nrm / trial_pos n*3 fp64, NULL = the patch's own. */
+void orc_score_at_batch(const orc_view *views, int n, const float *pos, const float *nrm,
+                        const int *ref, const int *nvis, const int *vis, int vstride,
+                        int cell_size, const double *trial_nrm, const double *trial_pos,
+                        float *ncc, uint8_t *tex, uint8_t *valid);
 void orc_filter_batch(const orc_view *views, int n, const float *pos, const float *nrm,
                       const int *ref, int *nvis, int *vis, int vstride, int cell_size, double thr,
                       int min_visible, uint8_t *keep);

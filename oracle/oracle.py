@@ -197,16 +197,31 @@ def axes_scale(views: Views, ref, nrm, pos):
     return xa, ya, dx.value
 
 
-def score_batch(views: Views, pos, nrm, ref, nvis, vis, cell_size, want_tex=False):
-    """Returns ncc (n, vstride) f32 [, tex (n, vstride, s, s, 3) u8, valid (n, vstride) u8]."""
+def score_batch(views: Views, pos, nrm, ref, nvis, vis, cell_size, want_tex=False,
+                trial_nrm=None, trial_pos=None):
+    """Returns ncc (n, vstride) f32 [, tex (n, vstride, s, s, 3) u8, valid (n, vstride) u8].
+    trial_nrm / trial_pos (n, 3) float64: GetProjectedTextures(normal, position, ...) -- the
+    stored pos stays the corner centre (patch.cpp:119-123)."""
     pos, nrm, ref, nvis, vis = _f32(pos), _f32(nrm), _i32(ref), _i32(nvis), _i32(vis)
     n, vs = vis.shape
     ncc = np.zeros((n, vs), np.float32)
     tex = np.zeros((n, vs, cell_size, cell_size, 3), np.uint8) if want_tex else None
     valid = np.zeros((n, vs), np.uint8) if want_tex else None
-    lib().orc_score_batch(views.arr, C.c_int(n), _p(pos), _p(nrm), _p(ref), _p(nvis), _p(vis),
-                          C.c_int(vs), C.c_int(cell_size), _p(ncc), _p(tex), _p(valid))
+    tn = None if trial_nrm is None else np.ascontiguousarray(trial_nrm, dtype=np.float64)
+    tp = None if trial_pos is None else np.ascontiguousarray(trial_pos, dtype=np.float64)
+    lib().orc_score_at_batch(views.arr, C.c_int(n), _p(pos), _p(nrm), _p(ref), _p(nvis), _p(vis),
+                             C.c_int(vs), C.c_int(cell_size), _p(tn), _p(tp), _p(ncc), _p(tex),
+                             _p(valid))
     return (ncc, tex, valid) if want_tex else ncc
+
+
+def unparametrize(views: Views, ref, nrm0, pos0, x):
+    """Optimization::UnparametrizePatch (optimization.cpp:78-96) -> (normal, position) fp64."""
+    nrm0, pos0 = _f32(nrm0), _f32(pos0)
+    n, p = np.zeros(3), np.zeros(3)
+    lib().orc_unparametrize(C.byref(views.arr[int(ref)]), _p(nrm0), _p(pos0), C.c_double(x[0]),
+                            C.c_double(x[1]), C.c_double(x[2]), _p(n), _p(p))
+    return n, p
 
 
 def filter_batch(views: Views, pos, nrm, ref, nvis, vis, cell_size, thr=0.6, min_visible=3):

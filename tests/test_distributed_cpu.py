@@ -55,6 +55,20 @@ class OracleLevelBackend:
         buf = torch.from_numpy(np.array(rows, np.int32).reshape(-1, self.words))
         return buf, len(rows)
 
+    def frontier_weights(self):
+        st = self.org.export()
+        w = np.zeros(self.V.n, np.int64)
+        for i in range(self.begin, self.org.size()):
+            if st["nvis"][i] >= 2:
+                w[st["ref"][i]] += st["nvis"][i]
+        return w
+
+    def commit_gathered(self, recv, world, capacity, counts):
+        parts = [recv[r * capacity: r * capacity + c] for r, c in enumerate(counts) if c > 0]
+        total = int(sum(counts))
+        records = torch.cat(parts) if parts else recv[:0]
+        return self.commit(records, total)
+
     def commit(self, records, total):
         n0 = self.org.size()
         rec = records.numpy()[:total]
@@ -65,7 +79,7 @@ class OracleLevelBackend:
         return self.org.size() - n0
 
 
-def _worker(rank, world, port, outdir):
+def _worker(rank, world, port, outdir, balance):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle import oracle as orc
@@ -79,7 +93,8 @@ def _worker(rank, world, port, outdir):
     prm = orc.default_params(minimum_visible_image=2)
     nvis, vis, _, _ = orc.visibility_batch(V, seeds["pos"], seeds["nrm"], seeds["ref"])
     be = OracleLevelBackend(orc, V, prm, seeds, nvis, vis)
-    rov = dd.partition_views(seeds["ref"], sc.n_views, world)
+    # fixed contiguous ownership, or re-balanced every level from the frontier (assign_views)
+    rov = None if balance else dd.partition_views(seeds["ref"], sc.n_views, world)
     stats = dd.expand_distributed(be, CELL, -1, rank, world, rov)
     ex = be.org.export()
     np.savez(os.path.join(outdir, f"rank{rank}.npz"), **ex,
@@ -100,8 +115,17 @@ def test_partition_views_is_contiguous_and_balanced():
 import pytest
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_multi_rank_expansion_matches_single_process_fifo(orc, world):
+def test_assign_views_is_deterministic_and_balanced():
+    w = np.array([50, 0, 7, 7, 30, 30, 1, 25], np.int64)
+    rov = dd.assign_views(w, 3)
+    assert np.array_equal(rov, dd.assign_views(w.copy(), 3)) and set(rov) <= {0, 1, 2}
+    load = np.array([w[rov == r].sum() for r in range(3)])
+    assert load.max() <= 1.34 * w.sum() / 3            # LPT bound 4/3 - 1/(3m)
+    assert (dd.assign_views(w, 1) == 0).all()
+
+
+@pytest.mark.parametrize("world,balance", [(2, False), (3, False), (2, True), (3, True)])
+def test_multi_rank_expansion_matches_single_process_fifo(orc, world, balance):
     sc, seeds = _scene()
     V = orc.Views(sc.P, sc.images)
     prm = orc.default_params(minimum_visible_image=2)
@@ -114,7 +138,8 @@ def test_multi_rank_expansion_matches_single_process_fifo(orc, world):
     assert ref_org.size() > n_seed
     with tempfile.TemporaryDirectory() as d:
         port = 29500 + (os.getpid() % 2000)
-        mp.spawn(_worker, args=(world, port + world, d), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, port + world + 10 * balance, d, balance), nprocs=world,
+                 join=True)
         got = [dict(np.load(os.path.join(d, f"rank{r}.npz"))) for r in range(world)]
     grids = np.concatenate([ref_org.grid(v).ravel() for v in range(sc.n_views)])
     for g in got:

@@ -73,11 +73,49 @@ def test_golden_textures_ncc_filter(capi_mod, golden_scoring):
         clean = ~diff.any(axis=(2, 3))
         clean = clean & clean[:, :1]
         assert np.abs(ncc[sm & clean] - g[f"ncc{s}"][sm & clean]).max() < 5e-6   # bar 1e-4
-        if diff.sum() == 0:
-            keep, fnvis, fvis = ctx.filter(g["pos"], g["nrm"], g["ref"], g["nvis"], g["vis"], s)
-            assert np.array_equal(keep, g[f"keep{s}"])
-            assert np.array_equal(fnvis, g[f"fnvis{s}"])
-            assert np.array_equal(fvis, g[f"fvis{s}"])
+        # the filter, for every patch whose textures are all clean (a tie texel may move a score
+        # across the threshold; those patches -- at most 3 -- are the only ones not compared)
+        pclean = ~diff.any(axis=(1, 2, 3))
+        assert pclean.sum() >= len(pclean) - 3
+        keep, fnvis, fvis = ctx.filter(g["pos"], g["nrm"], g["ref"], g["nvis"], g["vis"], s)
+        assert np.array_equal(keep[pclean], g[f"keep{s}"][pclean])
+        assert np.array_equal(fnvis[pclean], g[f"fnvis{s}"][pclean])
+        assert np.array_equal(fvis[pclean], g[f"fvis{s}"][pclean])
+    ctx.close()
+
+
+def test_golden_objective_textures(capi_mod, golden_scoring, golden_views, orc):
+    """GetProjectedTextures(normal, position, ...) at trial (depth, roll, pitch) points -- what
+    the refinement objective evaluates -- against cv2 (tests/golden/make_golden_objective.py).
+    The pure-depth points pin that the corners stay centred on the STORED position
+    (patch.cpp:119-123) while the trial position only rescales the quad."""
+    import os
+    from conftest import GOLDEN
+    go = dict(np.load(os.path.join(GOLDEN, "golden_objective.npz")))
+    g = golden_scoring
+    ctx = capi_mod.Context(0, capi_mod.default_params(minimum_visible_image=2))
+    ctx.set_views(g["P"], list(g["images"]), xaxes=g["xaxis"], centers=g["center"])
+    idx = go["patch"]
+    ties = 0
+    for s in (5, 7, 11):
+        for b, x in enumerate(go["x"]):
+            # UnparametrizePatch (optimization.cpp:78-96), bit-identical with the generator's
+            tn, tp = (np.array(v) for v in zip(*(
+                orc.unparametrize(golden_views, g["ref"][i], g["nrm"][i], g["pos"][i], x)
+                for i in idx)))
+            ncc, tex, valid = ctx.score_at(g["pos"][idx], g["nrm"][idx], g["ref"][idx],
+                                           g["nvis"][idx], g["vis"][idx], s, tn, tp)
+            assert np.array_equal(valid, go[f"valid_{s}"][:, b])
+            diff = (tex != go[f"tex_{s}"][:, b]) & valid.astype(bool)[:, :, None, None, None]
+            assert diff[:, :, 1:].sum() == 0 and diff[:, :, 0, 1:].sum() == 0   # ties: texel (0,0)
+            clean = diff.sum(axis=(1, 2, 3, 4)) == 0
+            ties += int((~clean).sum())
+            # the objective from the scores: mean of 1 - NCC in view order, 2 if < 2 views
+            nv = g["nvis"][idx]
+            f = np.array([(1.0 - ncc[a, 1:nv[a]].astype(np.float64)).sum() / max(nv[a] - 1, 1)
+                          if nv[a] >= 2 else 2.0 for a in range(len(idx))])
+            assert np.abs(f - go[f"f_{s}"][:, b])[clean].max() < 1e-6
+    assert ties <= 3
     ctx.close()
 
 
@@ -371,3 +409,79 @@ def test_dark_textures_with_inexact_fp32_centring(capi_mod, exact_orc):
                                             nvis[:n], vis[:n], 5)
     assert np.array_equal(ev, oev) and np.array_equal(p, op) and np.array_equal(nr, on)
     ctx.close()
+
+
+@pytest.fixture(scope="module", params=[64, 256])
+def wide_views(request, capi_mod, exact_orc):
+    """64 and 256 views (the view counts of BASELINE configs C4 / C5), all inside the visibility
+    cone: visible sets of > 32, > 64 and > 128 entries."""
+    from densepoints_b200 import scenes
+    nv = request.param
+    sc = scenes.make_plane_scene(seed=41 + nv, n_views=nv, width=176, height=132,
+                                 yaw_spread_deg=32.0)
+    seeds = scenes.make_seeds(sc, 640, seed=43 + nv, depth_noise=0.004, tilt_deg=6.0)
+    ctx = capi_mod.Context(0)
+    ctx.set_views(sc.P, sc.images)
+    V = exact_orc.Views(sc.P, sc.images)
+    nvis, vis, _, _ = exact_orc.visibility_batch(V, seeds["pos"], seeds["nrm"], seeds["ref"])
+    yield dict(sc=sc, seeds=seeds, ctx=ctx, V=V, nvis=nvis, vis=vis, nv=nv)
+    ctx.close()
+
+
+def test_wide_visible_sets_score_filter_refine(wide_views, exact_orc):
+    """Score / filter / refine with 64- and 256-view visible sets: the refine group kernel at
+    s = 7 and the warp-per-patch refine kernel at s = 11 and 16, >= 500 patches each."""
+    d = wide_views
+    sd = d["seeds"]
+    assert d["nvis"].max() > (32 if d["nv"] == 64 else 128)
+    assert (d["nvis"] > (32 if d["nv"] == 64 else 64)).mean() > 0.5
+    g_nvis, g_vis, _, _ = d["ctx"].visibility(sd["pos"], sd["nrm"], sd["ref"])
+    assert np.array_equal(g_nvis, d["nvis"]) and np.array_equal(g_vis, d["vis"])
+    a = (sd["pos"], sd["nrm"], sd["ref"], d["nvis"], d["vis"])
+    for s in (7, 11, 16):
+        ncc = d["ctx"].score(*a, s)
+        o_ncc = exact_orc.score_batch(d["V"], *a, s)
+        assert np.abs(ncc - o_ncc).max() < 1e-6
+        keep, nv, vi = d["ctx"].filter(*a, s)
+        o_keep, o_nv, o_vi = exact_orc.filter_batch(d["V"], *a, s, 0.6, 3)
+        assert np.array_equal(keep, o_keep) and np.array_equal(nv, o_nv) and np.array_equal(vi, o_vi)
+    n = 512
+    b = tuple(x[:n] for x in a)
+    for s in (7, 11, 16):
+        pos, nrm, ev, xb = d["ctx"].refine(*b, s)
+        o_pos, o_nrm, o_ev, o_xb = exact_orc.refine_batch(d["V"], *b, s)
+        assert np.array_equal(ev, o_ev)
+        assert np.array_equal(pos, o_pos) and np.array_equal(nrm, o_nrm)
+        assert ev.max() > 20
+
+
+def _refine_stats(sc, ref, pos, nrm, ev, o_pos, o_nrm, o_ev):
+    C = sc.centers[ref]
+    dd = np.abs(np.linalg.norm(pos.astype(np.float64) - C, axis=1) -
+                np.linalg.norm(o_pos.astype(np.float64) - C, axis=1))
+    da = angle_deg(nrm, o_nrm)
+    same = (ev == o_ev) & (pos == o_pos).all(1) & (nrm == o_nrm).all(1)
+    return same, dd, da
+
+
+def test_c1_refine_against_opencv_procedure_oracle(c1, orc):
+    """The CUDA refinement against the oracle in homography mode 0 -- cv::findHomography's DLT +
+    eigen-solve + cv::warpPerspective's inversion, the procedure pinned against cv2 -- on config
+    C1 (2 000 seeds, mu = 5).  The two can only part at an exact 1/64-px tie of texel (0,0)
+    (DESIGN.md section 2), where OpenCV's own answer is decided by rounding noise; such a patch
+    takes another Nelder-Mead trajectory.  Everything else must be bit-identical; the divergent
+    fraction is bounded here and reported in DESIGN.md."""
+    d = c1
+    sd = d["seeds"]
+    pos, nrm, ev, _ = d["ctx"].refine(sd["pos"], sd["nrm"], sd["ref"], d["nvis"], d["vis"], 5)
+    orc.set_homography_mode(0)
+    try:
+        o_pos, o_nrm, o_ev, _ = orc.refine_batch(d["V"], sd["pos"], sd["nrm"], sd["ref"], d["nvis"],
+                                                 d["vis"], 5)
+    finally:
+        orc.set_homography_mode(1)
+    same, dd, da = _refine_stats(d["sc"], sd["ref"], pos, nrm, ev, o_pos, o_nrm, o_ev)
+    print(f"C1 mode-0: identical {same.sum()} / {len(same)}, max |d depth| {dd.max():.3g}, "
+          f"max d normal {da.max():.3g} deg")
+    assert same.mean() >= 0.99
+    assert dd[same].max() == 0 and da[same].max() == 0

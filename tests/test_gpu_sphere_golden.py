@@ -29,9 +29,11 @@ def test_golden_sphere_textures_ncc_filter(golden_scoring_sphere):
         clean = ~diff.any(axis=(2, 3))
         clean = clean & clean[:, :1]
         assert np.abs(ncc[sm & clean] - g[f"ncc{s}"][sm & clean]).max() < 5e-6   # bar 1e-4
-        if diff.sum() == 0:
-            keep, fnvis, fvis = ctx.filter(g["pos"], g["nrm"], g["ref"], g["nvis"], g["vis"], s)
-            assert np.array_equal(keep, g[f"keep{s}"])
-            assert np.array_equal(fnvis, g[f"fnvis{s}"])
-            assert np.array_equal(fvis, g[f"fvis{s}"])
+        # the filter for every patch whose textures are all clean (at most 3 are not)
+        pclean = ~diff.any(axis=(1, 2, 3))
+        assert pclean.sum() >= len(pclean) - 3
+        keep, fnvis, fvis = ctx.filter(g["pos"], g["nrm"], g["ref"], g["nvis"], g["vis"], s)
+        assert np.array_equal(keep[pclean], g[f"keep{s}"][pclean])
+        assert np.array_equal(fnvis[pclean], g[f"fnvis{s}"][pclean])
+        assert np.array_equal(fvis[pclean], g[f"fvis{s}"][pclean])
     ctx.close()

@@ -116,3 +116,41 @@ def test_golden_sphere_textures_ncc_filter(orc, golden_scoring_sphere):
         assert np.array_equal(fnvis, g[f"fnvis{s}"])
         assert np.array_equal(fvis, g[f"fvis{s}"])
     assert g["valid3"].sum() < 0.75 * g["valid8"].sum()      # the empty-texture path is exercised
+
+
+def test_golden_refinement_objective(orc, golden_scoring, golden_views):
+    """PatchOptimizationOpenCVFunctor::calc at 16 (depth, roll, pitch) points per patch against
+    cv2 (tests/golden/make_golden_objective.py, an independent restatement of
+    optimization_opencv.cpp:14-39 / optimization.cpp:14-56,78-96 / patch.cpp:111-164).  The
+    pure-depth points pin that the corners are built around the STORED position
+    (patch.cpp:119-123) and the trial position only scales the quad: with the corners around
+    the trial position instead, these vectors fail at x[4:8]."""
+    import os
+    from conftest import GOLDEN
+    go = dict(np.load(os.path.join(GOLDEN, "golden_objective.npz")))
+    g = golden_scoring
+    orc.set_homography_mode(0)
+    idx = go["patch"]
+    ties = 0
+    for s in (5, 7, 11):
+        for b, x in enumerate(go["x"]):
+            # the textures at trial parameters: GetProjectedTextures(normal, position, ...)
+            tn, tp = zip(*(orc.unparametrize(golden_views, g["ref"][i], g["nrm"][i], g["pos"][i], x)
+                           for i in idx))
+            _, tex, valid = orc.score_batch(golden_views, g["pos"][idx], g["nrm"][idx],
+                                            g["ref"][idx], g["nvis"][idx], g["vis"][idx], s,
+                                            want_tex=True, trial_nrm=np.array(tn),
+                                            trial_pos=np.array(tp))
+            assert np.array_equal(valid, go[f"valid_{s}"][:, b])
+            diff = (tex != go[f"tex_{s}"][:, b]) & valid.astype(bool)[:, :, None, None, None]
+            # only texel (0,0) may differ: an exact tie of the 1/32-px rounding, decided inside
+            # OpenCV by the sign of its eigen-solver's noise (DESIGN.md section 2)
+            assert diff[:, :, 1:].sum() == 0 and diff[:, :, 0, 1:].sum() == 0
+            clean = diff.sum(axis=(1, 2, 3, 4)) == 0
+            ties += int((~clean).sum())
+            for a, i in enumerate(idx):
+                if clean[a]:
+                    f = orc.objective(golden_views, g["ref"][i], g["vis"][i, :g["nvis"][i]], s,
+                                      g["nrm"][i], g["pos"][i], x)
+                    assert abs(f - go[f"f_{s}"][a, b]) < 1e-12, (s, a, b)
+    assert ties <= 3, ties          # 1 of 3072 (patch, point, cell size) cases today

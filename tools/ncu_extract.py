@@ -1,14 +1,21 @@
 """Extract the tracked numbers from an `ncu -i X.ncu-rep --page raw --csv` export.
 
 usage: python tools/ncu_extract.py RAW.csv LABEL [--evals-refine N] [--source TEXT]
-  appends {LABEL: [per-kernel metric dicts]} to profiles/r01_ncu_set_full_extract.json and,
-  with --evals-refine, rewrites profiles/r01_refine_traffic.json (read by bench.py)."""
+                                    [--hbm-evals-score N --hbm-evals-refine M]
+  appends {LABEL: [per-kernel metric dicts]} to profiles/r02_ncu_set_full_extract.json and,
+  with --evals-refine, rewrites profiles/r02_refine_traffic.json; with --hbm-evals-score,
+  profiles/r02_hbm_traffic.json (both read by bench.py).  Each carries src_sha256 = the hash of
+  the CUDA sources in the tree (densepoints_b200.build.source_hash) -- run this on the same tree
+  the capture was made from; bench.py reports the numbers only while the hash still matches."""
 import argparse
 import csv
 import json
 import os
+import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from densepoints_b200.build import source_hash  # noqa: E402
 KEEP = ["Kernel Name", "gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size",
         "launch__block_size", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
@@ -29,7 +36,11 @@ def main():
     ap.add_argument("label")
     ap.add_argument("--evals-refine", type=int, default=0)
     ap.add_argument("--source", default="")
+    ap.add_argument("--hbm-evals-score", type=int, default=0)
+    ap.add_argument("--hbm-evals-refine", type=int, default=0)
+    ap.add_argument("--src-sha256", default="", help="hash printed by the profiled run (default: this tree)")
     a = ap.parse_args()
+    sha = a.src_sha256 or source_hash()
     rows = list(csv.reader(open(a.raw)))
     hdr, units = rows[0], rows[1]
     out = []
@@ -47,26 +58,48 @@ def main():
         d["warp_state_samples_pct"] = {k: round(100 * v / tot, 1)
                                        for k, v in sorted(stall.items(), key=lambda kv: -kv[1])[:10]}
         out.append(d)
-    p = os.path.join(ROOT, "profiles", "r01_ncu_set_full_extract.json")
+    p = os.path.join(ROOT, "profiles", "r02_ncu_set_full_extract.json")
     allp = json.load(open(p)) if os.path.exists(p) else {}
     allp[a.label] = out
     json.dump(allp, open(p, "w"), indent=1)
-    if a.evals_refine:
-        ref = [(r, d) for r, d in zip(rows[2:], out) if "refine" in d["Kernel Name"]]
+    to_bytes = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    to_ms = {"ms": 1.0, "us": 1e-3, "s": 1e3, "ns": 1e-6}
+
+    def pick(word):
+        ref = [(r, d) for r, d in zip(rows[2:], out) if word in d["Kernel Name"]]
         r, d = ref[-1]
         g = lambda k: float(r[hdr.index(k)])
-        to_bytes = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         dram = sum(g(k) * to_bytes[units[hdr.index(k)]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-        dur = g("gpu__time_duration.sum") * {"ms": 1.0, "us": 1e-3, "s": 1e3, "ns": 1e-6}[units[hdr.index("gpu__time_duration.sum")]]
+        dur = g("gpu__time_duration.sum") * to_ms[units[hdr.index("gpu__time_duration.sum")]]
+        return d, g, dram, dur
+
+    if a.hbm_evals_score:
+        ds, gs, dram_s, dur_s = pick("score")
+        t = {"workload": "bench.py roofline_hbm leg (64 views 1920x1080, 1.5 M patches, mu=7)",
+             "source": a.source or a.raw, "src_sha256": sha,
+             "score_kernel": ds["Kernel Name"].replace("void ", "").split("(")[0],
+             "score_dram_bytes_per_launch": dram_s, "score_evals_per_launch": a.hbm_evals_score,
+             "score_duration_ms_under_ncu": dur_s,
+             "score_warp_inst_per_launch": gs("smsp__inst_executed.sum")}
+        if a.hbm_evals_refine:
+            dr, gr, dram_r, dur_r = pick("refine")
+            t.update({"refine_kernel": dr["Kernel Name"].replace("void ", "").split("(")[0],
+                      "refine_dram_bytes_per_launch": dram_r,
+                      "refine_evals_per_launch": a.hbm_evals_refine,
+                      "refine_duration_ms_under_ncu": dur_r})
+        json.dump(t, open(os.path.join(ROOT, "profiles", "r02_hbm_traffic.json"), "w"), indent=1)
+        print(json.dumps(t, indent=1))
+    if a.evals_refine:
+        d, g, dram, dur = pick("refine")
         t = {"kernel": d["Kernel Name"].replace("void ", "").split("(")[0],
              "workload": "bench.py N=1 (1048576 seeds, 16 views 1280x960, mu=7)",
-             "source": a.source or a.raw,
+             "source": a.source or a.raw, "src_sha256": sha,
              "dram_bytes_per_launch": dram,
              "warp_inst_per_launch": g("smsp__inst_executed.sum"),
              "evals_per_launch": a.evals_refine,
              "issue_active_pct": g("smsp__issue_active.avg.pct_of_peak_sustained_active"),
              "duration_ms_under_ncu": dur}
-        json.dump(t, open(os.path.join(ROOT, "profiles", "r01_refine_traffic.json"), "w"), indent=1)
+        json.dump(t, open(os.path.join(ROOT, "profiles", "r02_refine_traffic.json"), "w"), indent=1)
         print(json.dumps(t, indent=1))
 
 
