@@ -2,6 +2,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -10,6 +11,7 @@
 #include "dp_context.h"
 #include "dp_kernels.cuh"
 #include "dp_group.cuh"
+#include "dp_lane.cuh"
 
 // ---------------------------------------------------------------------------------------
 // helpers
@@ -369,12 +371,37 @@ static int build_order(dp_context *ctx, const int32_t *nvis, const uint8_t *mask
   return DP_OK;
 }
 
+#ifndef DP_SCORE_LANE
+#define DP_SCORE_LANE 1   // cells up to 8x8: one patch per lane (dp_lane.cuh)
+#endif
 #ifndef DP_SCORE_GROUP
 #define DP_SCORE_GROUP 1  // cells up to 16x16: several patches per warp (dp_group.cuh)
 #endif
 
+// tuning / A-B runs only: DP_REFINE_KERNEL=group and DP_SCORE_KERNEL=group select the
+// 4-lanes-per-patch kernels instead of the one-patch-per-lane kernels (dp_lane.cuh)
+static bool env_is_group(const char *name) {
+  const char *e = getenv(name);
+  return e && strcmp(e, "group") == 0;
+}
+static bool use_lane_score() { return DP_SCORE_LANE && !env_is_group("DP_SCORE_KERNEL"); }
+
 template <bool TEX, bool FILT>
 static int launch_score(dp_context *ctx, const DpScoreArgs &a, int cell_size, cudaStream_t st) {
+  if (cell_size <= DP_LGROUP_MAX_CELL && use_lane_score()) {
+    const int32_t *order = nullptr;
+    int rc = build_order(ctx, a.p.nvis, nullptr, a.p.n, st, &order);
+    if (rc != DP_OK) return rc;
+    const long long per_cta = (long long)DP_LWARPS * 32;
+    const unsigned grid = (unsigned)((a.p.n + per_cta - 1) / per_cta);
+#define DP_LCASE(S) case S: dp_score_lane_kernel<S, TEX, FILT><<<grid, DP_LWARPS * 32, 0, st>>>(a, order); break
+    switch (cell_size) {
+      DP_LCASE(2); DP_LCASE(3); DP_LCASE(4); DP_LCASE(5); DP_LCASE(6); DP_LCASE(7); DP_LCASE(8);
+    }
+#undef DP_LCASE
+    ++ctx->launches;
+    return DP_OK;
+  }
   if (DP_SCORE_GROUP && cell_size <= DP_GROUP_MAX_CELL_SCORE) {
     const int32_t *order = nullptr;
     int rc = build_order(ctx, a.p.nvis, nullptr, a.p.n, st, &order);
@@ -499,6 +526,33 @@ static cudaError_t launch_refine_group(const DpRefineArgs &a, int sm_count, cuda
   return cudaGetLastError();
 }
 
+// One patch per lane (dp_lane.cuh), cells up to 8x8.
+#ifndef DP_REFINE_LANE
+#define DP_REFINE_LANE 1
+#endif
+#ifndef DP_LANE_MIN_PATCHES
+#define DP_LANE_MIN_PATCHES 131072
+#endif
+template <int S>
+static cudaError_t launch_refine_lane(const DpRefineArgs &a, int sm_count, cudaStream_t st) {
+  int per_sm = 1;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dp_refine_lane_kernel<S>,
+                                                                DP_LWARPS * 32, 0);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  const long long per_cta = (long long)DP_LWARPS * 32;
+  long long want = ((long long)a.p.n + per_cta - 1) / per_cta;
+  long long grid = std::min<long long>(want, (long long)sm_count * per_sm);
+  dp_refine_lane_kernel<S><<<(unsigned)grid, DP_LWARPS * 32, 0, st>>>(a);
+  return cudaGetLastError();
+}
+static bool use_lane_kernel() { return DP_REFINE_LANE && !env_is_group("DP_REFINE_KERNEL"); }
+// (tests lower the threshold through the environment to run the lane kernel on small batches)
+static long long lane_min_patches() {
+  const char *e = getenv("DP_LANE_MIN_PATCHES");
+  return e ? atoll(e) : (long long)DP_LANE_MIN_PATCHES;
+}
+
 extern "C" int dp_refine_dev(dp_context *ctx, dp_patch_dev *p, int cell_size, const uint8_t *mask,
                              int32_t *evals, double *xbest, void *stream) {
   int rc = check_patch_dev(ctx, p, cell_size);
@@ -519,9 +573,28 @@ extern "C" int dp_refine_dev(dp_context *ctx, dp_patch_dev *p, int cell_size, co
   a.eps = ctx->prm.nm_eps;
   a.work_counter = ctx->work_counter.as<unsigned int>();
   a.mask = mask;
+#ifdef DP_DEBUG_TRACE
+  {
+    static double *tr = nullptr;
+    if (!tr) cudaMalloc(&tr, (size_t)(1 << 20) * 64);
+    std::vector<double> init((size_t)p->n * 8, -7.0);
+    cudaMemcpy(tr, init.data(), init.size() * 8, cudaMemcpyHostToDevice);
+    a.trace = getenv("DP_REFINE_TRACE") ? tr : nullptr;
+  }
+#endif
   if ((rc = build_order(ctx, p->nvis, mask, p->n, st, &a.order)) != DP_OK) return rc;
   cudaError_t e;
-  if (DP_REFINE_GROUP && cell_size <= DP_GROUP_MAX_CELL_REFINE) {
+  // One patch per lane needs several patches per lane to keep its lanes busy (a lane runs its
+  // patches one after the other, ~65 evaluations each; with fewer than DP_LANE_MIN_PATCHES the
+  // tail dominates and the 4-lanes-per-patch kernel is faster).
+  if (cell_size <= DP_LGROUP_MAX_CELL && use_lane_kernel() && p->n >= lane_min_patches()) {
+    e = cudaSuccess;
+#define DP_LCASE(S) case S: e = launch_refine_lane<S>(a, ctx->sm_count, st); break
+    switch (cell_size) {
+      DP_LCASE(2); DP_LCASE(3); DP_LCASE(4); DP_LCASE(5); DP_LCASE(6); DP_LCASE(7); DP_LCASE(8);
+    }
+#undef DP_LCASE
+  } else if (DP_REFINE_GROUP && cell_size <= DP_GROUP_MAX_CELL_REFINE) {
     e = cudaSuccess;
 #define DP_GCASE(S) case S: e = launch_refine_group<DpCfgFor<S>>(a, ctx->sm_count, st); break
     switch (cell_size) {
@@ -542,6 +615,15 @@ extern "C" int dp_refine_dev(dp_context *ctx, dp_patch_dev *p, int cell_size, co
   }
   ++ctx->launches;
   DP_CUDA(ctx, e);
+#ifdef DP_DEBUG_TRACE
+  if (a.trace) {
+    cudaStreamSynchronize(st);
+    std::vector<double> out((size_t)p->n * 8);
+    cudaMemcpy(out.data(), a.trace, out.size() * 8, cudaMemcpyDeviceToHost);
+    FILE *f = fopen(getenv("DP_REFINE_TRACE"), "wb");
+    if (f) { fwrite(out.data(), 8, out.size(), f); fclose(f); }
+  }
+#endif
   return dp_scratch_release(ctx, st);
 }
 

@@ -194,6 +194,32 @@ __device__ __forceinline__ void dp_write_setup(DpViewSetupG &R, double m0, doubl
   R.ok = ok ? 1 : 0;
 }
 
+// cv::findHomography on 4 points is the exact projective map quad -> [0,s]^2 and
+// cv::warpPerspective uses its inverse; that inverse (cell -> quad) has the closed form below
+// (unit square -> quadrilateral): no 9x9 eigen-solve, no 3x3 inversion.  Outputs the six
+// non-trivial coefficients of source = (m0 x + m1 y + 32 qx0, m3 x + m4 y + 32 qy0) /
+// (m6 x + m7 y + 1) in 1/32-px units; false for a degenerate quad or non-finite coefficients.
+__device__ __forceinline__ bool dp_quad_map(double qx0, double qy0, double qx1, double qy1,
+                                            double qx2, double qy2, double qx3, double qy3,
+                                            double inv_s, double &m0, double &m1, double &m3,
+                                            double &m4, double &m6, double &m7) {
+  const double sxq = qx0 - qx1 + qx2 - qx3, syq = qy0 - qy1 + qy2 - qy3;
+  const double dx1 = qx1 - qx2, dx2 = qx3 - qx2, dy1 = qy1 - qy2, dy2 = qy3 - qy2;
+  const double den = dx1 * dy2 - dx2 * dy1;
+  const double rden = 1.0 / den;
+  const double gq = (sxq * dy2 - dx2 * syq) * rden;
+  const double hq = (dx1 * syq - sxq * dy1) * rden;
+  m0 = 32.0 * (qx1 - qx0 + gq * qx1) * inv_s;
+  m1 = 32.0 * (qx3 - qx0 + hq * qx3) * inv_s;
+  m3 = 32.0 * (qy1 - qy0 + gq * qy1) * inv_s;
+  m4 = 32.0 * (qy3 - qy0 + hq * qy3) * inv_s;
+  m6 = gq * inv_s;
+  m7 = hq * inv_s;
+  const bool fin = isfinite(m0) && isfinite(m1) && isfinite(m3) && isfinite(m4) && isfinite(m6) &&
+                   isfinite(m7);
+  return fin && (den != 0.0);
+}
+
 #define DP_ROUND 16  // views whose set-up records are resident at once (per warp)
 
 // GL = lanes that share one patch (32: the whole warp; 8: four patches per warp, each group of
@@ -243,24 +269,10 @@ __device__ __forceinline__ void dp_setup_views(const DpViewDev *__restrict__ vie
     const double qx1 = (double)__shfl_sync(DP_FULL, fx, 1, 4), qy1 = (double)__shfl_sync(DP_FULL, fy, 1, 4);
     const double qx2 = (double)__shfl_sync(DP_FULL, fx, 2, 4), qy2 = (double)__shfl_sync(DP_FULL, fy, 2, 4);
     const double qx3 = (double)__shfl_sync(DP_FULL, fx, 3, 4), qy3 = (double)__shfl_sync(DP_FULL, fy, 3, 4);
-    // cv::findHomography on 4 points is the exact projective map quad -> [0,s]^2 and
-    // cv::warpPerspective uses its inverse; that inverse (cell -> quad) has the closed form
-    // below (unit square -> quadrilateral): no 9x9 eigen-solve, no 3x3 inversion.
-    const double sxq = qx0 - qx1 + qx2 - qx3, syq = qy0 - qy1 + qy2 - qy3;
-    const double dx1 = qx1 - qx2, dx2 = qx3 - qx2, dy1 = qy1 - qy2, dy2 = qy3 - qy2;
-    const double den = dx1 * dy2 - dx2 * dy1;
-    const double rden = 1.0 / den;
-    const double gq = (sxq * dy2 - dx2 * syq) * rden;
-    const double hq = (dx1 * syq - sxq * dy1) * rden;
+    double m0, m1, m3, m4, m6, m7;
+    const bool mapped = dp_quad_map(qx0, qy0, qx1, qy1, qx2, qy2, qx3, qy3, inv_s, m0, m1, m3, m4, m6, m7);
     if (c == 0 && active) {
-      const double m0 = 32.0 * (qx1 - qx0 + gq * qx1) * inv_s;
-      const double m1 = 32.0 * (qx3 - qx0 + hq * qx3) * inv_s;
-      const double m3 = 32.0 * (qy1 - qy0 + gq * qy1) * inv_s;
-      const double m4 = 32.0 * (qy3 - qy0 + hq * qy3) * inv_s;
-      const double m6 = gq * inv_s, m7 = hq * inv_s;
-      const bool fin = isfinite(m0) && isfinite(m1) && isfinite(m3) && isfinite(m4) && isfinite(m6) &&
-                       isfinite(m7);
-      const bool ok = all_in && rw > 0 && rh > 0 && (den != 0.0) && fin;  // optimization.cpp:45
+      const bool ok = all_in && rw > 0 && rh > 0 && mapped;  // optimization.cpp:45
       dp_write_setup(recs[k], m0, m1, 32.0 * qx0, m3, m4, 32.0 * qy0, m6, m7,
                      V->img + (ok ? (size_t)tly * V->pitch_px + tlx : 0), V->pitch_px, rw, rh, ok);
     }

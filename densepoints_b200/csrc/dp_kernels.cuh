@@ -229,6 +229,9 @@ struct DpRefineArgs {
   unsigned int *work_counter;  // zeroed before launch
   const uint8_t *mask;         // optional: refine only patches with mask[i] != 0
   const int32_t *order;        // optional: work item k = patch order[k] (longest-first schedule)
+#ifdef DP_DEBUG_TRACE
+  double *trace;               // debug builds: objective value of the first 8 evaluations, n*8
+#endif
 };
 
 // Longest-processing-time-first schedule for the persistent refine warps: the cost of a

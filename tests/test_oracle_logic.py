@@ -149,3 +149,39 @@ def test_scene_is_deterministic():
     assert np.array_equal(a.P, b.P) and all(np.array_equal(x, y) for x, y in zip(a.images, b.images))
     sa, sb = scenes.make_seeds(a, 10, seed=1), scenes.make_seeds(b, 10, seed=1)
     assert all(np.array_equal(sa[k], sb[k]) for k in sa)
+
+
+def test_downhill_frozen_trajectories(orc):
+    """Every point the solver evaluates, in order, against the frozen vectors of
+    tests/golden/make_golden_downhill.py (drift guard: upstream OpenCV cannot be run here)."""
+    import json
+    import os
+    import sys
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, here)
+    import make_golden_downhill as mg
+    want = json.load(open(os.path.join(here, "golden_downhill.json")))
+    for name in mg.CASES:
+        got = mg.run(name)
+        assert got["fcount"] == want[name]["fcount"], name
+        assert got["points"] == want[name]["points"], name      # bit-exact doubles via JSON repr
+        assert got["x"] == want[name]["x"] and got["res"] == want[name]["res"]
+    # the piecewise-constant case really exercises ties and the shrink step
+    q = want["quantised3"]
+    vals = [mg.objective("quantised3")(np.array(p)) for p in q["points"]]
+    assert len(set(vals)) < len(vals)
+    assert want["capped3"]["fcount"] >= 60
+
+
+def test_downhill_upstream_regression_cases(orc):
+    """The two cases of upstream OpenCV's own regression test, AS RECALLED from
+    modules/core/test/test_downhill_simplex.cpp (the file is not available offline, so this is a
+    recollection, not a copy): SphereF from (1,1) with step (-0.5,-0.5) -> (0,0), RosenbrockF
+    from (0,0) with step (0.5,0.5) -> (1,1); default TermCriteria(MAX_ITER+EPS, 5000, 1e-6);
+    tolerance 1e-2 on the minimiser and the minimum."""
+    sphere = lambda x: float(x[0] * x[0] + x[1] * x[1])
+    x, res, fc = orc.downhill(sphere, [1.0, 1.0], [-0.5, -0.5], max_evals=5000, eps=1e-6)
+    assert abs(res) < 1e-2 and np.abs(x).max() < 1e-2
+    rosen = lambda x: float(100 * (x[1] - x[0] ** 2) ** 2 + (1 - x[0]) ** 2)
+    x, res, fc = orc.downhill(rosen, [0.0, 0.0], [0.5, 0.5], max_evals=5000, eps=1e-6)
+    assert abs(res) < 1e-2 and np.abs(x - 1.0).max() < 1e-2

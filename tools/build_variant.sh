@@ -10,5 +10,5 @@ nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -X
   -Xptxas -v -o "$ROOT/densepoints_b200/_variants/$name.so" densepoints_cuda.cu > "/tmp/build_variant_$name.log" 2>&1 \
   || { grep -i "error" "/tmp/build_variant_$name.log" | head -5; echo "BUILD FAILED <- $name"; exit 1; }
 cat "/tmp/build_variant_$name.log" \
-  | grep -A2 "dp_refine_group_kernelI10DpGroupCfgILi4ELi13E\|dp_refine_group_kernelI10DpGroupCfgILi8ELi16E" | grep "spill\|Used" | tr '\n' ' '
+  | grep -A2 "dp_refine_group_kernelI10DpGroupCfgILi4ELi13E\|dp_refine_lane_kernelILi7E" | grep "spill\|Used" | tr '\n' ' '
 echo " <- $name"
