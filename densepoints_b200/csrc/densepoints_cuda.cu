@@ -576,8 +576,9 @@ extern "C" int dp_refine_dev(dp_context *ctx, dp_patch_dev *p, int cell_size, co
 #ifdef DP_DEBUG_TRACE
   {
     static double *tr = nullptr;
-    if (!tr) cudaMalloc(&tr, (size_t)(1 << 20) * 64);
-    std::vector<double> init((size_t)p->n * 8, -7.0);
+    if (!tr) cudaMalloc(&tr, (size_t)(1 << 20) * 64 + 64);
+    std::vector<double> init((size_t)p->n * 8 + 8, -7.0);
+    memset(init.data() + (size_t)p->n * 8, 0, 64);
     cudaMemcpy(tr, init.data(), init.size() * 8, cudaMemcpyHostToDevice);
     a.trace = getenv("DP_REFINE_TRACE") ? tr : nullptr;
   }
@@ -618,8 +619,13 @@ extern "C" int dp_refine_dev(dp_context *ctx, dp_patch_dev *p, int cell_size, co
 #ifdef DP_DEBUG_TRACE
   if (a.trace) {
     cudaStreamSynchronize(st);
-    std::vector<double> out((size_t)p->n * 8);
+    std::vector<double> out((size_t)p->n * 8 + 8);
     cudaMemcpy(out.data(), a.trace, out.size() * 8, cudaMemcpyDeviceToHost);
+    {
+      const unsigned long long *c = reinterpret_cast<const unsigned long long *>(out.data() + (size_t)p->n * 8);
+      fprintf(stderr, "lane census: textured %llu empty %llu fewer-views %llu tail %llu unstaged %llu of %llu slots\n",
+              c[0], c[1], c[2], c[3], c[4], c[5]);
+    }
     FILE *f = fopen(getenv("DP_REFINE_TRACE"), "wb");
     if (f) { fwrite(out.data(), 8, out.size(), f); fclose(f); }
   }

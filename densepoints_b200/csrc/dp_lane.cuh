@@ -188,15 +188,19 @@ __device__ __forceinline__ bool nml_step(const DpNmLane &S, int &state, int &idx
 }
 
 // Optimization::UnparametrizePatch (optimization.cpp:78-96), every lane for its own patch.
-__device__ __forceinline__ void dp_unparametrize_l(const double C[3], const double n0[3],
-                                                   const double p0[3], double depth, double roll,
-                                                   double pitch, double n[3], double p[3]) {
-  const double k = xadd(1.0, depth);
+// Out of line and with one rolled sincos site: it runs once per evaluation (not per view) from
+// two places, and the refine kernel is instruction-cache sensitive (ncu r2l: 16 % of the warp
+// samples waited for instructions).
+__device__ __noinline__ void dp_unparametrize_l(const double C[3], const double n0[3],
+                                                const double p0[3], const double x[3], double n[3],
+                                                double p[3]) {
+  const double k = xadd(1.0, x[0]);
 #pragma unroll
   for (int j = 0; j < 3; ++j) p[j] = xadd(C[j], xmul(k, xsub(p0[j], C[j])));
-  double sa, ca, sb, cb;
-  sincos(roll, &sa, &ca);
-  sincos(pitch, &sb, &cb);
+  double sn[2], cs[2];
+#pragma unroll 1
+  for (int a = 0; a < 2; ++a) sincos(x[1 + a], &sn[a], &cs[a]);
+  const double sa = sn[0], ca = cs[0], sb = sn[1], cb = cs[1];
   n[0] = xadd(xmul(cb, n0[0]), xmul(-sb, n0[2]));
   n[1] = xadd(xadd(xmul(xmul(sa, sb), n0[0]), xmul(ca, n0[1])), xmul(xmul(cb, sa), n0[2]));
   n[2] = xadd(xadd(xmul(xmul(ca, sb), n0[0]), xmul(-sa, n0[1])), xmul(xmul(ca, cb), n0[2]));
@@ -209,6 +213,8 @@ struct DpLaneView {
   const uint32_t *src;                    // first pixel of the ROI
   int pitch, rw, rh;
   bool ok;
+  bool tame;  // every source coordinate of the cell is finite and far inside the int32 range:
+              // the texel loop may round with the magic-number add instead of cvt.rni (below)
 };
 
 __device__ __forceinline__ void dp_lane_setup(const DpViewDev *__restrict__ views, int n_views,
@@ -253,6 +259,13 @@ __device__ __forceinline__ void dp_lane_setup(const DpViewDev *__restrict__ view
   R.rw = rw;
   R.rh = rh;
   R.ok = ok;
+  // W = m6 x + m7 y + 1 is linear over the cell [0, s-1]^2, so its minimum is at a corner; the
+  // numerators are bounded by their coefficient sums.  W >= 2^-6 and |num| < 2^22 give
+  // |coordinate| < 2^28: rint() by adding 1.5 * 2^52 is then exact and nothing saturates.
+  const double e = (double)(s - 1);
+  const double wmin = 1.0 + fmin(0.0, m6 * e) + fmin(0.0, m7 * e);
+  const double nx = (fabs(m0) + fabs(m1)) * e + fabs(R.M2), ny = (fabs(m3) + fabs(m4)) * e + fabs(R.M5);
+  R.tame = ok && (wmin >= 0.015625) && (nx < 4194304.0) && (ny < 4194304.0);
 }
 
 // Blend of the four taps with OpenCV's 15-bit weights and BGR -> gray, as dp_texel_blend, with
@@ -310,8 +323,18 @@ __device__ __forceinline__ void dp_lane_texels(const DpLaneView &R, const uint32
       const double r = dp_rcp(Wd);  // W == 0 -> NaN coordinates -> cvt gives 0 (see dp_texel_fetch)
       const double fX = fma(R.M0, xd, A) * r;
       const double fY = fma(R.M3, xd, B) * r;
-      const int Xi = __double2int_rn(fX);  // saturate_cast<int>(cvRound), half to even
-      const int Yi = __double2int_rn(fY);
+      // saturate_cast<int>(cvRound(.)), half to even.  The staged loop only runs for "tame" views
+      // (DpLaneView::tame: |coordinate| < 2^28, finite), where adding 1.5 * 2^52 leaves the
+      // round-to-nearest-even integer in the low word -- one FP64 add instead of a conversion
+      // on the (quarter-rate) XU pipe; the generic loop keeps the saturating cvt.rni.
+      int Xi, Yi;
+      if (STAGED) {
+        Xi = __double2loint(fX + 6755399441055744.0);
+        Yi = __double2loint(fY + 6755399441055744.0);
+      } else {
+        Xi = __double2int_rn(fX);
+        Yi = __double2int_rn(fY);
+      }
       const int Xc = max(min(Xi, xmax), 0), Yc = max(min(Yi, ymax), 0);  // BORDER_REPLICATE
       const int x0 = Xc >> 5, y0 = Yc >> 5;
       const uint32_t *r0 = tp + (unsigned)(y0 * tpitch + x0), *r1 = r0 + tpitch;
@@ -339,6 +362,9 @@ __device__ __forceinline__ void dp_lane_texels(const DpLaneView &R, const uint32
 
 // sum_i fl32(a_i - fl32(mean_a)) * fl32(b_i - fl32(mean_b)) in fp64, texel by texel in row-major
 // order (error_measurements.cpp:54 on CV_32F operands, Mat::dot's order).
+// (Measured and dropped: an fp64-only variant for textures whose fp32 centring is provably exact
+// -- no I2F / F2F on the XU pipe -- with this loop as the fallback: 5 % of the lane-views fail
+// the exactness test, so nearly every warp ran both loops; refine 3.31 -> 3.09 G evals/s.)
 template <int S>
 __device__ __forceinline__ double dp_lane_numerator(const uint2 *ga, const uint2 *gb, float mfa,
                                                     float mfb) {
@@ -357,33 +383,30 @@ __device__ __forceinline__ double dp_lane_numerator(const uint2 *ga, const uint2
   return num;
 }
 
-// Stage the ROIs of the warp's 32 lanes into their tiles.  Lane pairs work together: both lanes
-// copy first the even lane's tile, then the odd lane's, taking alternate 16-byte pieces of a
-// row, so that two neighbouring pieces travel in one L2 request.  Returns (for the calling
-// lane) whether ITS ROI was staged; the tile row pitch is 4 * pieces pixels.  Completion:
-// cp.async.wait_all + __syncwarp().
-__device__ __forceinline__ bool dp_lane_stage(const DpLaneView &R, bool want, uint32_t *warp_tiles,
-                                              int lane, int &tpitch, int &xoff) {
+// Stage the lane's ROI into its tile: one 16-byte cp.async per 4-pixel piece of a row, from the
+// ROI origin rounded down to 4 pixels (16-byte alignment; the taps carry the 0-3 pixel offset).
+// The tile row pitch is 4 * pieces pixels.  Returns whether the ROI fits the tile (else the taps
+// come straight from the image).  Completion: cp.async.wait_all (the tile is lane-private).
+// (Measured and dropped: lane pairs splitting each other's rows so that neighbouring pieces
+// share an L2 request -- 4 shuffles and two nested loops per view cost 17.7 of 172 warp
+// instructions per evaluation, ncu r2l; this form is ~2.)
+__device__ __forceinline__ bool dp_lane_stage(const DpLaneView &R, bool want, uint32_t *tile,
+                                              int &tpitch, int &xoff) {
   // image rows are 128-byte aligned: the pixel offset of the ROI inside its 16-byte quad is
   // visible in the pointer
   xoff = (int)((reinterpret_cast<uintptr_t>(R.src) >> 2) & 3u);
   const int pieces = (R.rw + xoff + 3) >> 2;
   tpitch = 4 * pieces;
   const bool fits = want && tpitch * R.rh <= DP_LTILE;
-  const unsigned long long srcv = reinterpret_cast<unsigned long long>(R.src - xoff);
-  const int desc = fits ? (R.rh | (pieces << 8)) : 0;
-#pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    const int owner = (lane & ~1) + t;
-    const unsigned long long s_o = __shfl_sync(DP_FULL, srcv, owner);
-    const int d_o = __shfl_sync(DP_FULL, desc, owner);
-    const int ip_o = __shfl_sync(DP_FULL, R.pitch, owner);
-    const int rh_o = d_o & 0xff, pc_o = d_o >> 8;
-    const uint32_t *g = reinterpret_cast<const uint32_t *>(s_o);
-    uint32_t *d = warp_tiles + owner * DP_LTSTR;
-    for (int r = 0; r < rh_o; ++r)
-      for (int q = lane & 1; q < pc_o; q += 2)
-        dp_cp_async16(d + r * 4 * pc_o + 4 * q, g + (size_t)r * ip_o + 4 * q);
+  if (fits) {
+    const uint32_t *g = R.src - xoff;
+    uint32_t *d = tile;
+    for (int r = 0; r < R.rh; ++r, g += R.pitch, d += tpitch) {
+      dp_cp_async16(d, g);
+      if (pieces > 1) dp_cp_async16(d + 4, g + 4);
+      if (pieces > 2) dp_cp_async16(d + 8, g + 8);
+      for (int q = 3; q < pieces; ++q) dp_cp_async16(d + 4 * q, g + 4 * q);
+    }
   }
   return fits;
 }
@@ -424,6 +447,7 @@ dp_score_lane_kernel(DpScoreArgs a, const int32_t *__restrict__ order) {
   const int nvmax = __reduce_max_sync(DP_FULL, nv);
   unsigned a1 = 0, a2 = 0;
   bool a_ok = false;
+  float mfa = 0.f;
   int wcur = 0, prev = -1;
   const double thr = a.thr;
 #pragma unroll 1
@@ -432,11 +456,9 @@ dp_score_lane_kernel(DpScoreArgs a, const int32_t *__restrict__ order) {
     const int vid = active ? vis[k] : -1;
     DpLaneView R;
     dp_lane_setup(a.p.views, a.p.n_views, vid, active, S, inv_s, f, R);
-    __syncwarp();  // every lane is done with the tiles of the previous view
     int tpitch, xoff;
-    const bool staged = dp_lane_stage(R, R.ok, warp_tiles, lane, tpitch, xoff);
+    const bool staged = dp_lane_stage(R, R.ok && R.tame, warp_tiles + lane * DP_LTSTR, tpitch, xoff);
     dp_cp_async_wait_all();
-    __syncwarp();
     unsigned s1 = 0, s2 = 0;
     uint2 *g = (k == 0) ? gA : gB;
     if (R.ok) {
@@ -451,10 +473,11 @@ dp_score_lane_kernel(DpScoreArgs a, const int32_t *__restrict__ order) {
       a1 = s1;
       a2 = s2;
       a_ok = R.ok;
+      mfa = (float)xmul((double)a1, scale);
     } else if (active) {
       double score = -1.0;  // an empty texture (error_measurements.cpp:38-40)
       if (R.ok && a_ok) {
-        const float mfa = (float)xmul((double)a1, scale), mfb = (float)xmul((double)s1, scale);
+        const float mfb = (float)xmul((double)s1, scale);
         const double num = dp_lane_numerator<S>(gA, gB, mfa, mfb);
         score = dp_ncc_finish(a1, a2, s1, s2, num, scale, npx);
       }
@@ -498,6 +521,11 @@ __global__ void __launch_bounds__(DP_LWARPS * 32, DP_LMINCTA) dp_refine_lane_ker
 #pragma unroll 1
   for (;;) {
     // ---- 1. lanes without a patch take the next ones from the work counter --------------------
+    // (a.order hands the patches out by descending view count, so the lanes of a warp mostly
+    // evaluate the same number of views.  Measured and dropped: one queue per view-count class
+    // with every warp staying inside a class -- no lane ever idles through a neighbour's extra
+    // view, but the longest-first order is lost and the classes with many views finish last:
+    // refine 3.61 -> 3.35 G evals/s.)
     for (;;) {
       const unsigned need = __ballot_sync(DP_FULL, !have && !exhausted);
       if (need == 0) break;
@@ -544,7 +572,10 @@ __global__ void __launch_bounds__(DP_LWARPS * 32, DP_LMINCTA) dp_refine_lane_ker
     // ---- 2. one objective evaluation per lane, in lockstep -------------------------------------
     // PatchOptimizationOpenCVFunctor::calc (optimization_opencv.cpp:14-39)
     double n[3], p[3];
-    dp_unparametrize_l(c3, n0, p0, NM.pt(0), NM.pt(1), NM.pt(2), n, p);
+    {
+      const double x[3] = {NM.pt(0), NM.pt(1), NM.pt(2)};
+      dp_unparametrize_l(c3, n0, p0, x, n, p);
+    }
     const int nv_eval = (have && nv >= 2 && ref_ok) ? nv : 0;
     DpFrame f;
     dp_make_frame(a.p.views + (ref_ok ? ref : 0), S, n, p, p0, f);  // corners stay around p0
@@ -552,18 +583,34 @@ __global__ void __launch_bounds__(DP_LWARPS * 32, DP_LMINCTA) dp_refine_lane_ker
     double sum = 0.0;
     unsigned a1 = 0, a2 = 0;
     bool a_ok = false;
+    float mfa = 0.f;
 #pragma unroll 1
     for (int k = 0; k < nvmax; ++k) {
       const bool active = k < nv_eval;
       DpLaneView R;
       dp_lane_setup(a.p.views, a.p.n_views, active ? vis[k] : -1, active, S, inv_s, f, R);
-      __syncwarp();  // every lane is done with the tiles of the previous view
       int tpitch, xoff;
-      const bool staged = dp_lane_stage(R, R.ok, warp_tiles, lane, tpitch, xoff);
+      const bool staged = dp_lane_stage(R, R.ok && R.tame, warp_tiles + lane * DP_LTSTR, tpitch, xoff);
       dp_cp_async_wait_all();
-      __syncwarp();
       unsigned s1 = 0, s2 = 0;
       uint2 *g = (k == 0) ? gA : gB;
+#ifdef DP_DEBUG_TRACE
+      if (a.trace) {  // lane-slot census of this view step: [0] textured, [1] empty texture,
+                      // [2] patch has fewer views, [3] tail (no patch left), [4] unstaged
+        const unsigned m0 = __ballot_sync(DP_FULL, R.ok), m1 = __ballot_sync(DP_FULL, active && !R.ok),
+                       m2 = __ballot_sync(DP_FULL, have && !active), m3 = __ballot_sync(DP_FULL, !have),
+                       m4 = __ballot_sync(DP_FULL, R.ok && !staged);
+        if (lane == 0) {
+          unsigned long long *c = reinterpret_cast<unsigned long long *>(a.trace) + (size_t)8 * a.p.n;
+          atomicAdd(c + 0, (unsigned long long)__popc(m0));
+          atomicAdd(c + 1, (unsigned long long)__popc(m1));
+          atomicAdd(c + 2, (unsigned long long)__popc(m2));
+          atomicAdd(c + 3, (unsigned long long)__popc(m3));
+          atomicAdd(c + 4, (unsigned long long)__popc(m4));
+          atomicAdd(c + 5, 32ull);
+        }
+      }
+#endif
       if (R.ok) {
         if (staged)
           dp_lane_texels<S, true>(R, warp_tiles + lane * DP_LTSTR + xoff, tpitch, g, s1, s2);
@@ -574,10 +621,11 @@ __global__ void __launch_bounds__(DP_LWARPS * 32, DP_LMINCTA) dp_refine_lane_ker
         a1 = s1;
         a2 = s2;
         a_ok = R.ok;
+        mfa = (float)xmul((double)a1, scale);
       } else if (active) {
         double score = -1.0;  // an empty texture (error_measurements.cpp:38-40)
         if (R.ok && a_ok) {
-          const float mfa = (float)xmul((double)a1, scale), mfb = (float)xmul((double)s1, scale);
+          const float mfb = (float)xmul((double)s1, scale);
           const double num = dp_lane_numerator<S>(gA, gB, mfa, mfb);
           score = dp_ncc_finish(a1, a2, s1, s2, num, scale, npx);
         }
@@ -599,7 +647,8 @@ __global__ void __launch_bounds__(DP_LWARPS * 32, DP_LMINCTA) dp_refine_lane_ker
         // best vertex -> one more trip through UnparametrizePatch, then write back;
         // SetNormal / SetPosition store fp32 (patch.h:38-53)
         double nb[3], pb[3];
-        dp_unparametrize_l(c3, n0, p0, NM.pt(0), NM.pt(1), NM.pt(2), nb, pb);
+        const double xb[3] = {NM.pt(0), NM.pt(1), NM.pt(2)};
+        dp_unparametrize_l(c3, n0, p0, xb, nb, pb);
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
           if (ref_ok) {
