@@ -206,6 +206,16 @@ __device__ __noinline__ void dp_unparametrize_l(const double C[3], const double 
   n[2] = xadd(xadd(xmul(xmul(ca, sb), n0[0]), xmul(-sa, n0[1])), xmul(xmul(ca, cb), n0[2]));
 }
 
+#ifndef DP_LANE_PROJECT_OOL
+#define DP_LANE_PROJECT_OOL 1
+#endif
+// View::ProjectPoint out of line for the lane kernels' set-up (4 call sites, two fp64 divisions
+// each): the refine kernel is instruction-cache sensitive.
+__device__ __noinline__ void dp_project_ool(const double *__restrict__ P, double X0, double X1,
+                                            double X2, double *uv) {
+  dp_project(P, X0, X1, X2, uv[0], uv[1]);
+}
+
 // Per-lane set-up of one view (patch.cpp:111-164 up to the homography): what dp_setup_views
 // computes with four lanes and shuffles, here straight-line code of one lane.
 struct DpLaneView {
@@ -233,7 +243,14 @@ __device__ __forceinline__ void dp_lane_setup(const DpViewDev *__restrict__ view
     const double X0 = xadd(xadd(f.p[0], sgx * f.ax[0]), sgy * f.ay[0]);
     const double X1 = xadd(xadd(f.p[1], sgx * f.ax[1]), sgy * f.ay[1]);
     const double X2 = xadd(xadd(f.p[2], sgx * f.ax[2]), sgy * f.ay[2]);
+#if DP_LANE_PROJECT_OOL
+    double uv[2];
+    dp_project_ool(V->P, X0, X1, X2, uv);
+    u[c] = uv[0];
+    v[c] = uv[1];
+#else
     dp_project(V->P, X0, X1, X2, u[c], v[c]);
+#endif
     all_in = all_in && (u[c] > 0) && (u[c] < (double)W) && (v[c] > 0) && (v[c] < (double)H);
     // ROI: tl = min ceil, br = max floor over the 4 corners (patch.cpp:137-140)
     tlx = min(tlx, __double2int_ru(u[c]));
