@@ -232,16 +232,32 @@ def run_expansion_and_hbm(args, rank, world, local_rank, dev):
     seed_s = time.perf_counter() - t0
     be = dd.CudaLevelBackend(ctx, dev)
 
-    def one_run():
+    def one_run(ownership="ranges"):
         ctx.organizer_reset()
         acc = ctx.organizer_insert(pos[m], nrm[m], seeds["ref"][m], fnvis[m], fvis[m])
         tm = {}
         sync()
         t1 = time.perf_counter()
-        st = dd.expand_distributed(be, EXP_CELL, EXP_MAX_LEVELS, rank, world, None, timings=tm)
+        st = dd.expand_distributed(be, EXP_CELL, EXP_MAX_LEVELS, rank, world, None, timings=tm,
+                                   ownership=ownership)
         sync()
         return st, tm, time.perf_counter() - t1, int(acc.sum())
 
+    # for the record: strict ownership by reference image (re-balanced per level); its speed-up is
+    # bounded by the heaviest view of the frontier
+    by_view = None
+    if world > 1:
+        one_run("views")
+        st_v, tm_v, wall_v, _ = one_run("views")
+        dg_v, _ = store_digest(ctx)
+        tv_v = torch.tensor([tm_v["local_ms"], tm_v["allgather_ms"], tm_v["commit_ms"]],
+                            dtype=torch.float64, device=dev)
+        lmin_v = tv_v[0].clone()
+        dist.all_reduce(tv_v, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lmin_v, op=dist.ReduceOp.MIN)
+        by_view = {"expansion_ms": float((tv_v[0] + tv_v[1] + tv_v[2]).sum().item()),
+                   "local_ms_max_rank": tv_v[0].tolist(), "local_ms_min_rank": lmin_v.tolist(),
+                   "store_sha256": dg_v}
     one_run()                                            # warm-up (allocations, NCCL channels)
     st, tm, wall_s, seeded = one_run()
     digest, n_store = store_digest(ctx)
@@ -268,8 +284,10 @@ def run_expansion_and_hbm(args, rank, world, local_rank, dev):
                        f"(mu={EXP_SEED_CELL} filter + refine), Expand::ExpandPatches at mu={EXP_CELL}, "
                        f"level cap {EXP_MAX_LEVELS}",
            "scaling": "strong", "n_gpus": world,
-           "sharding": "patches by reference image (ownership re-balanced per level by the "
-                       "frontier's work per view), one NCCL allgather of candidate records per level",
+           "sharding": "the frontier's parents in N contiguous ranges of equal work (sum of visible-view "
+                       "counts), cut identically on every rank from the replicated store; one NCCL "
+                       "allgather of candidate records per level",
+           "by_reference_image": by_view,
            "levels": L, "seeds_kept": int(m.sum()), "seeds_inserted": seeded,
            "patches": n_store, "candidates_refined": int(cand_total), "records_gathered": st["passed"],
            "inserted": st["inserted"], "record_bytes": ctx.record_bytes(),

@@ -192,10 +192,17 @@ __global__ void dp_u8_to_u32_kernel(const uint8_t *__restrict__ in, unsigned int
 }
 
 // K5a: which frontier parents expand: >= 2 visible views (expand.cpp:69) and owned by `rank`.
+// Ownership: rank_of_view[reference image] when a table is given; else (world > 1) the frontier
+// is cut into `world` contiguous ranges of equal work -- wscan = exclusive scan of the parents'
+// weights (their visible-view counts, 0 if they do not expand), wtotal its total: parent i
+// belongs to rank floor(wscan[i] * world / wtotal).  Every rank computes the same cut from the
+// replicated store.
 __global__ void dp_parent_flags_kernel(const int32_t *__restrict__ nvis,
                                        const int32_t *__restrict__ ref, long long begin,
                                        long long n_f, const int32_t *__restrict__ rank_of_view,
-                                       int rank, int n_views, unsigned int *__restrict__ flags) {
+                                       const unsigned int *__restrict__ wscan,
+                                       unsigned long long wtotal, int world, int rank, int n_views,
+                                       unsigned int *__restrict__ flags) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_f) return;
   const long long p = begin + i;
@@ -203,8 +210,17 @@ __global__ void dp_parent_flags_kernel(const int32_t *__restrict__ nvis,
   if (f && rank_of_view) {
     const int r = ref[p];
     f = (r >= 0 && r < n_views) && rank_of_view[r] == rank;
+  } else if (f && wscan) {
+    f = (int)(((unsigned long long)wscan[i] * (unsigned long long)world) / wtotal) == rank;
   }
   flags[i] = f ? 1u : 0u;
+}
+__global__ void dp_parent_weights_kernel(const int32_t *__restrict__ nvis, long long begin,
+                                         long long n_f, unsigned int *__restrict__ w) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_f) return;
+  const int nv = nvis[begin + i];
+  w[i] = nv >= 2 ? (unsigned int)nv : 0u;
 }
 
 // Work of the frontier per reference view: sum of the visible-view counts of the parents that
@@ -672,19 +688,30 @@ extern "C" int dp_expand_level_local(dp_context *ctx, int cell_size, int rank, i
   const DpViewDev *views = ctx->d_views.as<DpViewDev>();
   // ownership table on the device
   const int32_t *d_rov = nullptr;
-  if (world > 1) {
-    if (!rank_of_view) return dp_fail(ctx, DP_ERR_INVALID_ARG, "rank_of_view is null");
+  if (world > 1 && rank_of_view) {
     DP_CUDA(ctx, ctx->s_misc.ensure((size_t)nviews * 8));
     DP_CUDA(ctx, cudaMemcpyAsync(ctx->s_misc.ptr, rank_of_view, (size_t)nviews * 4,
                                  cudaMemcpyHostToDevice, st));
     d_rov = ctx->s_misc.as<int32_t>();
   }
   // K5a + scan: compact the expanding parents
-  DP_CUDA(ctx, ctx->e_count.ensure(((size_t)nf + 1) * 8));
+  DP_CUDA(ctx, ctx->e_count.ensure(((size_t)nf + 1) * 16));
   unsigned int *pflags = ctx->e_count.as<unsigned int>();
   unsigned int *pslot = pflags + (nf + 1);
+  const unsigned int *wscan = nullptr;
+  long long wtotal = 0;
+  if (world > 1 && !rank_of_view) {  // equal-work contiguous ranges of the frontier
+    unsigned int *w = pslot + (nf + 1), *ws = w + (nf + 1);
+    dp_parent_weights_kernel<<<(unsigned)((nf + 255) / 256), 256, 0, st>>>(o.nvis.as<int32_t>(), fb, nf, w);
+    ++ctx->launches;
+    if ((rc = dp_exclusive_scan(ctx, w, ws, nf, st)) != DP_OK) return rc;
+    if ((rc = dp_scan_total(ctx, w, ws, nf, st, &wtotal)) != DP_OK) return rc;
+    if (wtotal == 0) return dp_scratch_release(ctx, st);
+    wscan = ws;
+  }
   dp_parent_flags_kernel<<<(unsigned)((nf + 255) / 256), 256, 0, st>>>(
-      o.nvis.as<int32_t>(), o.ref.as<int32_t>(), fb, nf, d_rov, rank, nviews, pflags);
+      o.nvis.as<int32_t>(), o.ref.as<int32_t>(), fb, nf, d_rov, wscan, (unsigned long long)wtotal,
+      world, rank, nviews, pflags);
   ++ctx->launches;
   rc = dp_exclusive_scan(ctx, pflags, pslot, nf, st);
   if (rc != DP_OK) return rc;

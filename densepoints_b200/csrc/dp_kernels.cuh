@@ -365,11 +365,29 @@ __device__ __forceinline__ void nm_shrink_vertex(DpNelderMead &S, int lane, int 
   __syncwarp();
 }
 
-template <int NPASS>
+// WPP = warps per patch.  1: every warp refines its own patch (large batches).  4: the views of
+// a patch are dealt out to four warps (view k >= 1 goes to warp (k - 1) mod 4, every warp also
+// computes the anchor texture it scores against); the warps exchange their scores through shared
+// memory (two named barriers per evaluation), then each of them sums the objective in view order
+// and advances its own copy of the Nelder-Mead state -- identical values everywhere, no
+// cross-warp solver traffic.  For batches that leave most of the machine idle (the late, small
+// levels of an expansion, or one GPU's share of a level when the frontier is split over eight):
+// the time of such a launch is the LATENCY of its longest patch (up to 500 dependent evaluations
+// of up to ~50 views each), which four warps cut almost four-fold.
+#define DP_MW_MAXV 256  // largest visible set the multi-warp form handles
+__device__ __forceinline__ void dp_group_barrier(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int NPASS, int WPP = 1>
 __global__ void __launch_bounds__(DP_RWARPS * 32, dp_refine_min_ctas(NPASS)) dp_refine_kernel(DpRefineArgs a) {
   __shared__ DpWarpShared<NPASS, false> wsh[DP_RWARPS];
   __shared__ DpNelderMead nm[DP_RWARPS];
+  __shared__ double gscore[WPP > 1 ? DP_RWARPS / WPP : 1][WPP > 1 ? DP_MW_MAXV : 1];
+  __shared__ int32_t gvis[WPP > 1 ? DP_RWARPS : 1][WPP > 1 ? DP_MW_MAXV / WPP + 2 : 1];
+  __shared__ unsigned int gitem[DP_RWARPS / WPP];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = warp / WPP, wg = warp % WPP;  // the warp's patch slot in the CTA, its share of it
   const int s = a.p.s, npx = s * s;
   DpTexels<NPASS> tx;
   tx.init(s, lane);
@@ -378,18 +396,31 @@ __global__ void __launch_bounds__(DP_RWARPS * 32, dp_refine_min_ctas(NPASS)) dp_
   enum { ST_INIT, ST_REFLECT, ST_EXPAND, ST_CONTRACT, ST_SHRINK, ST_DONE };
   for (;;) {
     unsigned int iu = 0;
-    if (lane == 0) iu = atomicAdd(a.work_counter, 1u);
-    iu = __shfl_sync(DP_FULL, iu, 0);
+    if (WPP == 1) {
+      if (lane == 0) iu = atomicAdd(a.work_counter, 1u);
+      iu = __shfl_sync(DP_FULL, iu, 0);
+    } else {
+      if (wg == 0 && lane == 0) gitem[grp] = atomicAdd(a.work_counter, 1u);
+      dp_group_barrier(1 + grp, WPP * 32);
+      iu = gitem[grp];
+      dp_group_barrier(1 + grp, WPP * 32);
+    }
     if (iu >= (unsigned int)a.p.n) break;
     const long long i = a.order ? (long long)a.order[iu] : (long long)iu;
     if (a.mask != nullptr && a.mask[i] == 0) {  // removed by Seed::RemovePatches (seed.cpp:146-156)
-      if (a.evals && lane == 0) a.evals[i] = 0;
+      if (a.evals && lane == 0 && wg == 0) a.evals[i] = 0;
       continue;
     }
     const int nv = min(a.p.nvis[i], a.p.vstride);
     const int ref = a.p.ref[i];
     const bool ref_ok = ref >= 0 && ref < a.p.n_views;
     const int32_t *vis = a.p.vis + (size_t)i * a.p.vstride;
+    int nvw = nv;  // this warp's views: all of them, or the anchor and every WPP-th other view
+    if (WPP > 1) {
+      nvw = nv >= 1 ? 1 + (nv - 1 - wg + WPP - 1) / WPP : 0;
+      if (nv - 1 - wg < 0) nvw = nv >= 1 ? 1 : 0;
+      for (int t = lane; t < nvw; t += 32) gvis[warp][t] = t == 0 ? vis[0] : vis[1 + wg + (t - 1) * WPP];
+    }
     __syncwarp();
     if (lane == 0) {
       // createInitialSimplex: v_i = x0 + step_{i-1}/2 e_{i-1}, then v_0 = x0 - step/2; x0 = 0
@@ -421,7 +452,7 @@ __global__ void __launch_bounds__(DP_RWARPS * 32, dp_refine_min_ctas(NPASS)) dp_
       }
       if (state == ST_DONE) {
         // SetNormal / SetPosition store fp32 (patch.h:38-53)
-        if (lane < 3) {
+        if (lane < 3 && wg == 0) {
           const double nv_ = lane == 0 ? n[0] : (lane == 1 ? n[1] : n[2]);
           const double pv_ = lane == 0 ? p[0] : (lane == 1 ? p[1] : p[2]);
           if (ref_ok) {
@@ -430,21 +461,33 @@ __global__ void __launch_bounds__(DP_RWARPS * 32, dp_refine_min_ctas(NPASS)) dp_
           }
           if (a.xbest) a.xbest[3 * i + lane] = S.pt[lane];
         }
-        if (a.evals && lane == 0) a.evals[i] = fcount;
+        if (a.evals && lane == 0 && wg == 0) a.evals[i] = fcount;
         break;
       }
       // ---- the single objective call site: PatchOptimizationOpenCVFunctor::calc ----------
       double fval = 2.0;  // scores.size() == 0 (optimization_opencv.cpp:30-32)
       if (nv >= 2 && ref_ok) {
         double sum = 0.0;
-        dp_eval_views<NPASS, false, false>(
-            a.p.views, a.p.n_views, ref, vis, nv, s, npx, n, p, p0, tx, ws, lane, nullptr,
-            nullptr, [&](int k0, int kc, double score) {
-              // std::accumulate of (1 - NCC) in view order (optimization_opencv.cpp:24, 34)
-              const double term = xsub(1.0, score);
-              for (int l = (k0 == 0 ? 1 : 0); l < kc; ++l)
-                sum = xadd(sum, __shfl_sync(DP_FULL, term, l));
-            });
+        if (WPP == 1) {
+          dp_eval_views<NPASS, false, false>(
+              a.p.views, a.p.n_views, ref, vis, nv, s, npx, n, p, p0, tx, ws, lane, nullptr,
+              nullptr, [&](int k0, int kc, double score) {
+                // std::accumulate of (1 - NCC) in view order (optimization_opencv.cpp:24, 34)
+                const double term = xsub(1.0, score);
+                for (int l = (k0 == 0 ? 1 : 0); l < kc; ++l)
+                  sum = xadd(sum, __shfl_sync(DP_FULL, term, l));
+              });
+        } else {
+          dp_eval_views<NPASS, false, false>(
+              a.p.views, a.p.n_views, ref, gvis[warp], nvw, s, npx, n, p, p0, tx, ws, lane, nullptr,
+              nullptr, [&](int k0, int kc, double score) {
+                const int t = k0 + lane;  // entry of this warp's list -> view 1 + wg + (t - 1) WPP
+                if (lane < kc && t >= 1) gscore[grp][1 + wg + (t - 1) * WPP] = score;
+              });
+          dp_group_barrier(1 + grp, WPP * 32);
+          for (int k = 1; k < nv; ++k) sum = xadd(sum, xsub(1.0, gscore[grp][k]));  // view order
+          dp_group_barrier(1 + grp, WPP * 32);
+        }
         fval = sum / (double)(nv - 1);
       }
       // ---- consume it according to the Nelder-Mead state ---------------------------------

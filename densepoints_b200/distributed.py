@@ -141,13 +141,17 @@ def gather_records(buf: torch.Tensor, n_local: int, world: int):
 
 
 def expand_distributed(backend, cell_size: int, max_levels: int, rank: int, world: int,
-                       rank_of_view=None, timings=None) -> dict:
+                       rank_of_view=None, timings=None, ownership="views") -> dict:
     """Expand::ExpandPatches (reference expand.cpp:34-101) across `world` ranks.  The
     organizer must hold the same seeds on every rank (dp_organizer_insert on each).
-    rank_of_view: a fixed ownership table (partition_views), or None = re-balanced every level
-    from the frontier's work per reference view (assign_views).  timings (optional dict): per
-    level lists local_ms / allgather_ms / commit_ms and the record counts, when the backend can
-    time its stream."""
+    Ownership of a level's parents:
+      rank_of_view given      a fixed table by reference image (partition_views);
+      ownership == "views"    by reference image, re-balanced every level from the frontier's
+                              work per view (assign_views) -- bounded by the heaviest view;
+      ownership == "ranges"   `world` contiguous ranges of the frontier with equal work, cut
+                              inside the library (dp_expand_level_local with a NULL table).
+    timings (optional dict): per level lists local_ms / allgather_ms / commit_ms and the record
+    counts, when the backend can time its stream."""
     stats = dict(levels=0, pops=0, passed=0, inserted=0, local_records=0)
     level = 0
     can_time = timings is not None and hasattr(backend, "mark")
@@ -161,7 +165,7 @@ def expand_distributed(backend, cell_size: int, max_levels: int, rank: int, worl
         if nf <= 0:
             break
         rov = rank_of_view
-        if rov is None and world > 1:
+        if rov is None and world > 1 and ownership == "views":
             rov = assign_views(backend.frontier_weights(), world)
         t0 = backend.mark() if can_time else None
         buf, n_local = backend.local(cell_size, rank, world, rov, 4 * nf)

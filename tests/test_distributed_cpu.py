@@ -38,8 +38,16 @@ class OracleLevelBackend:
     def local(self, cell_size, rank, world, rov, max_records):
         st = self.org.export()
         rows = []
+        own = None
+        if world > 1 and rov is None:        # equal-work contiguous ranges (dp_parent_flags_kernel)
+            w = np.where(st["nvis"][self.begin:] >= 2, st["nvis"][self.begin:], 0).astype(np.int64)
+            scan = np.cumsum(w) - w
+            own = (scan * world) // max(int(w.sum()), 1)
         for i in range(self.begin, self.org.size()):
-            if st["nvis"][i] < 2 or (world > 1 and rov[st["ref"][i]] != rank):
+            if st["nvis"][i] < 2:
+                continue
+            if world > 1 and (own[i - self.begin] != rank if own is not None
+                              else rov[st["ref"][i]] != rank):
                 continue
             kids = self.orc.expand_patch(self.V, self.prm, cell_size, st["pos"][i], st["nrm"][i],
                                          st["ref"][i], st["vis"][i, :st["nvis"][i]])
@@ -94,8 +102,10 @@ def _worker(rank, world, port, outdir, balance):
     nvis, vis, _, _ = orc.visibility_batch(V, seeds["pos"], seeds["nrm"], seeds["ref"])
     be = OracleLevelBackend(orc, V, prm, seeds, nvis, vis)
     # fixed contiguous ownership, or re-balanced every level from the frontier (assign_views)
+    # (equal-work ranges of the frontier: ownership="ranges", the table stays None)
     rov = None if balance else dd.partition_views(seeds["ref"], sc.n_views, world)
-    stats = dd.expand_distributed(be, CELL, -1, rank, world, rov)
+    stats = dd.expand_distributed(be, CELL, -1, rank, world, rov,
+                                  ownership="ranges" if balance == 2 else "views")
     ex = be.org.export()
     np.savez(os.path.join(outdir, f"rank{rank}.npz"), **ex,
              grids=np.concatenate([be.org.grid(v).ravel() for v in range(sc.n_views)]),
@@ -124,7 +134,7 @@ def test_assign_views_is_deterministic_and_balanced():
     assert (dd.assign_views(w, 1) == 0).all()
 
 
-@pytest.mark.parametrize("world,balance", [(2, False), (3, False), (2, True), (3, True)])
+@pytest.mark.parametrize("world,balance", [(2, 0), (3, 0), (2, 1), (3, 1), (2, 2), (3, 2)])
 def test_multi_rank_expansion_matches_single_process_fifo(orc, world, balance):
     sc, seeds = _scene()
     V = orc.Views(sc.P, sc.images)
@@ -138,7 +148,7 @@ def test_multi_rank_expansion_matches_single_process_fifo(orc, world, balance):
     assert ref_org.size() > n_seed
     with tempfile.TemporaryDirectory() as d:
         port = 29500 + (os.getpid() % 2000)
-        mp.spawn(_worker, args=(world, port + world + 10 * balance, d, balance), nprocs=world,
+        mp.spawn(_worker, args=(world, port + world + 10 * int(balance), d, balance), nprocs=world,
                  join=True)
         got = [dict(np.load(os.path.join(d, f"rank{r}.npz"))) for r in range(world)]
     grids = np.concatenate([ref_org.grid(v).ravel() for v in range(sc.n_views)])
