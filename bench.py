@@ -180,6 +180,48 @@ def workload_name(args):
             f"{args.seeds} seed patches per GPU, Seed::FilterPatches + OptimizePatches, mu=7")
 
 
+def run_mirror_e2e(sc, seeds, steps):
+    """The same step through the C++ host mirror of the reference's classes on a
+    std::vector<Patch> in pageable memory (tools/e2e_mirror_bench.cpp): what a maintainer's
+    SeedCUDA::OptimizeAndRefinePatches() call costs end to end.  Rank 0, N = 1 only."""
+    import tempfile
+    from densepoints_b200 import build as dpbuild
+    lib = dpbuild.build_cuda()
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = os.path.join(tmp, "e2e_mirror_bench")
+        env = dict(os.environ)
+        env.pop("CC", None)
+        env.pop("CXX", None)
+        r = subprocess.run(["g++", "-std=c++14", "-O2", "-I" + os.path.join(ROOT, "densepoints_b200", "host"),
+                            "-I" + os.path.join(ROOT, "include"),
+                            os.path.join(ROOT, "tools", "e2e_mirror_bench.cpp"), "-o", exe,
+                            "-L" + os.path.dirname(lib), "-ldensepoints_cuda",
+                            "-Wl,-rpath," + os.path.dirname(lib)], env=env, capture_output=True, text=True)
+        if r.returncode != 0:
+            return {"error": "g++: " + r.stderr[-300:]}
+        dump = os.path.join(tmp, "scene.bin")
+        with open(dump, "wb") as f:
+            f.write(np.array([sc.n_views, sc.width, sc.height], np.int32).tobytes())
+            for P, im in zip(sc.P, sc.images):
+                f.write(np.ascontiguousarray(P, np.float64).tobytes())
+                f.write(np.ascontiguousarray(im, np.uint8).tobytes())
+            n = len(seeds["ref"])
+            f.write(np.array([n], np.int32).tobytes())
+            f.write(np.ascontiguousarray(seeds["pos"], np.float32).tobytes())
+            f.write(np.ascontiguousarray(seeds["nrm"], np.float32).tobytes())
+            f.write(np.ascontiguousarray(seeds["ref"], np.int32).tobytes())
+        r = subprocess.run([exe, dump, str(CELL), str(steps)], capture_output=True, text=True, timeout=900)
+        if r.returncode != 0:
+            return {"error": (r.stderr or r.stdout)[-300:]}
+        out = json.loads(r.stdout.strip().splitlines()[-1])
+    return {"value": out["evals"] / out["seconds"], "unit": UNIT,
+            "refined_patches_per_s": out["refined"] / out["seconds"], "steps": out["steps"],
+            "ms_per_step": 1e3 * out["seconds"] / out["steps"],
+            "what": "SeedCUDA::OptimizeAndRefinePatches() of the C++ host mirror on a "
+                    "std::vector<Patch> (pageable): Patch -> SoA marshalling, dp_filter_refine, "
+                    "write-back into the Patch objects, RemovePatches"}
+
+
 EXP_VIEWS, EXP_W, EXP_H, EXP_SEEDS, EXP_SEED_CELL, EXP_CELL, EXP_MAX_LEVELS = 64, 1920, 1080, 50_000, 16, 11, 12
 
 
@@ -595,6 +637,12 @@ def main():
                          f"(OpenMP); {dt:.1f} s",
                "refined_patches_per_s": float(m.sum()) / dt}
 
+    mirror = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            mirror = run_mirror_e2e(sc, seeds, max(1, min(args.steps, 3)))
+        except Exception as ex:
+            mirror = {"error": repr(ex)}
     launches_main = launches
     ctx.close()
     del pos0, nrm0, ref, nvis0, vis0, pos, nrm, nvis, vis, keep, evals, flush
@@ -617,7 +665,7 @@ def main():
                                  "timed region"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                        "refined_patches_per_s": e2e_refined_per_s},
+                        "refined_patches_per_s": e2e_refined_per_s, "cxx_mirror_pageable": mirror},
                 "gpu_launches": launches_main, "clocks": clocks, "roofline": roofline,
                 "cpu_baseline": cpu, "expansion": expansion, "roofline_hbm": hbm_leg}
         print(json.dumps(line), flush=True)

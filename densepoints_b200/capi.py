@@ -161,6 +161,17 @@ class Context:
                                           _ptr(im), C.c_int(w), C.c_int(h),
                                           C.c_size_t(im.strides[0])), "dp_upload_view")
 
+    def set_num_views(self, n):
+        self._ck(lib().dp_set_num_views(self._h, C.c_int(n)), "dp_set_num_views")
+
+    def upload_view(self, i, P, image):
+        """One view at a time (after set_num_views): large image sets need not sit on the host."""
+        P = np.ascontiguousarray(P, dtype=np.float64).reshape(12)
+        im = np.ascontiguousarray(image, dtype=np.uint8)
+        h, w = im.shape[:2]
+        self._ck(lib().dp_upload_view(self._h, C.c_int(i), _ptr(P), None, None, _ptr(im), C.c_int(w),
+                                      C.c_int(h), C.c_size_t(im.strides[0])), "dp_upload_view")
+
     def num_views(self):
         return lib().dp_num_views(self._h)
 

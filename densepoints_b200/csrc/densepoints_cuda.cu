@@ -509,15 +509,19 @@ static cudaError_t launch_refine_wpp(const DpRefineArgs &a, int sm_count, cudaSt
   dp_refine_kernel<NPASS, WPP><<<(unsigned)grid, DP_RWARPS * 32, 0, st>>>(a);
   return cudaGetLastError();
 }
-// Batches that cannot fill the machine with one warp per patch (fewer patches than resident
-// warps) and whose visible sets fit the exchange buffer run four warps per patch: such a launch
-// lasts as long as its longest patch, and four warps shorten that latency almost four-fold.
-// DP_REFINE_WPP=1 forces one warp per patch (A/B runs).
+// Batches that cannot keep the machine busy for long with one warp per patch run four warps,
+// or a whole CTA of eight, per patch (visible sets up to DP_MW_MAXV views): such a launch lasts
+// about as long as its longest patch -- up to 500 dependent evaluations -- and k warps shorten
+// that latency almost k-fold.  Measured on the 64-view expansion (bench.py, 8 GPUs): levels with
+// ~5 000 candidates per GPU took 10-12 ms with one warp per patch whatever their size, the
+// levels below 2 400 candidates 2-4 ms with four.  DP_REFINE_WPP=1 forces one warp per patch.
 template <int NPASS>
 static cudaError_t launch_refine(const DpRefineArgs &a, int sm_count, cudaStream_t st) {
   const char *e = getenv("DP_REFINE_WPP");
-  const bool allow_mw = !(e && atoi(e) == 1);
-  if (allow_mw && a.p.vstride <= DP_MW_MAXV && (long long)a.p.n <= (long long)sm_count * 16)
+  const bool allow_mw = !(e && atoi(e) == 1) && a.p.vstride <= DP_MW_MAXV;
+  if (allow_mw && (long long)a.p.n <= (long long)sm_count * 4)
+    return launch_refine_wpp<NPASS, 8>(a, sm_count, st);
+  if (allow_mw && (long long)a.p.n <= (long long)sm_count * 64)
     return launch_refine_wpp<NPASS, 4>(a, sm_count, st);
   return launch_refine_wpp<NPASS, 1>(a, sm_count, st);
 }

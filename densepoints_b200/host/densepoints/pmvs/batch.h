@@ -44,10 +44,11 @@ struct PatchBatch {
     }
   }
   void StoreVisible(Patch *const *patches) const {
+    ImagesIndices v;  // one buffer for the whole batch: the assignment below reuses the patch's storage
     for (int i = 0; i < soa.n; ++i) {
-      ImagesIndices v;
+      v.clear();
       for (int k = 0; k < nvis[i]; ++k) v.push_back((size_t)vis[(size_t)i * soa.vstride + k]);
-      patches[i]->SetTrullyVisibleImages(v);
+      if (v != patches[i]->GetTrullyVisibleImages()) patches[i]->SetTrullyVisibleImages(v);
     }
   }
   void StoreColor(Patch *const *patches) const {

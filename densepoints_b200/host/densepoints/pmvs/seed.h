@@ -5,6 +5,7 @@
 #ifndef DENSEPOINTS_B200_PMVS_SEED
 #define DENSEPOINTS_B200_PMVS_SEED
 
+#include <utility>
 #include <vector>
 
 #include "densepoints/pmvs/optimization.h"
@@ -105,12 +106,20 @@ class SeedCUDA {
     session_->Check(dp_refine(session_->ctx(), &b.soa, (int)cell_size_, nullptr, evals_.data(), nullptr), "dp_refine");
     b.StoreGeometry(ptr.data());
   }
-  void RemovePatches(const std::vector<size_t> &patch_indices) {  // seed.cpp:146-156
-    size_t remove_offset = 0;
-    for (size_t index_to_remove : patch_indices) {
-      patches_.erase(patches_.begin() + (index_to_remove - remove_offset));
-      ++remove_offset;
+  // seed.cpp:146-156 erases the listed patches one by one (ascending indices, order kept) --
+  // quadratic in the batch size.  Same result, one stable pass.
+  void RemovePatches(const std::vector<size_t> &patch_indices) {
+    if (patch_indices.empty()) return;
+    size_t w = 0, k = 0;
+    for (size_t i = 0; i < patches_.size(); ++i) {
+      if (k < patch_indices.size() && patch_indices[k] == i) {
+        ++k;
+        continue;
+      }
+      if (w != i) patches_[w] = std::move(patches_[i]);
+      ++w;
     }
+    patches_.resize(w);
   }
   const std::vector<int32_t> &LastEvals() const { return evals_; }
 

@@ -198,6 +198,36 @@ def make_plane_scene(seed=1, n_views=3, width=640, height=480, f=None, distance=
                  centers=np.array(centers))
 
 
+def lattice_plane_cameras(nx=16, ny=16, spacing=4.0, height=20.0, width=3840, height_px=2160,
+                          f=3000.0, tilt_deg=20.0, seed=5):
+    """BASELINE configs[4] style cameras: an nx x ny lattice `height` above the textured ground
+    plane z = 0 (the cameras sit at z < 0 like everywhere in this module), each looking down at a
+    point up to +-tilt_deg off its nadir.  Returns (P (V,3,4), centers, Rs, f, cx, cy, extent,
+    texture): everything but the images, which render_plane_view() makes one at a time (256 views
+    of 3840x2160 are 6.4 GB as BGR)."""
+    cx, cy = width / 2.0, height_px / 2.0
+    rng = np.random.default_rng(seed)
+    centers, Rs, Ps = [], [], []
+    for j in range(ny):
+        for i in range(nx):
+            c = np.array([(i - (nx - 1) / 2.0) * spacing, (j - (ny - 1) / 2.0) * spacing, -height])
+            t = np.tan(np.deg2rad(tilt_deg)) * height
+            target = np.array([c[0] + rng.uniform(-t, t) * 0.5, c[1] + rng.uniform(-t, t) * 0.5, 0.0])
+            R = look_at(c, target)
+            centers.append(c)
+            Rs.append(R)
+            Ps.append(projection(f, cx, cy, R, c))
+    extent = 0.5 * max(nx, ny) * spacing + height * width / f
+    px_world = height / f
+    tex = Texture3D(seed + 1000, (3.0 * px_world, 14.0 * px_world))
+    return np.array(Ps), np.array(centers), Rs, f, cx, cy, extent, tex
+
+
+def render_plane_view(center, R, f, cx, cy, width, height, extent, tex, device):
+    """One view of the plane scene on a torch device (see _render_torch)."""
+    return _render_torch([center], [R], f, cx, cy, width, height, "plane", extent, tex, device)[0]
+
+
 def make_sphere_scene(seed=2, n_views=16, width=1280, height=960, f=1000.0, radius=5.0,
                       distance=20.0, cap_deg=32.0, name="C2-sphere", only_views=None):
     """Configs C2/C3: textured sphere, `n_views` cameras on a spherical cap

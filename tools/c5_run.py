@@ -1,0 +1,128 @@
+"""BASELINE configs[4] (C5) style run: 256 views 3840x2160 (8.5 GB of packed images per GPU),
+200 000 seeds, exactly 3 expansion levels, patches sharded over the ranks with one NCCL
+allgather per level.  Run under torchrun with one rank per GPU (any N, also plain python for
+N = 1).  Reports time per level, bytes allgathered per level, device memory in use, the store
+size and the sha256 of store + grids (identical on every rank and for every N).
+
+torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 tools/c5_run.py
+"""
+import argparse
+import hashlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from densepoints_b200 import capi, scenes  # noqa: E402
+from densepoints_b200 import distributed as dd  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--grid", type=int, default=16)            # grid x grid cameras
+    ap.add_argument("--width", type=int, default=3840)
+    ap.add_argument("--seeds", type=int, default=200_000)
+    ap.add_argument("--levels", type=int, default=3)
+    ap.add_argument("--out", default="")
+    a = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W, H = a.width, a.width * 9 // 16
+    f = 3000.0 * W / 3840.0
+    P, centers, Rs, f, cx, cy, extent, tex = scenes.lattice_plane_cameras(
+        nx=a.grid, ny=a.grid, width=W, height_px=H, f=f)
+    V = len(P)
+    ctx = capi.Context(local)
+    ctx.set_num_views(V)
+    free0 = torch.cuda.mem_get_info()[0]
+    t0 = time.perf_counter()
+    for v in range(V):                       # render on the owner, replicate, upload, forget
+        if v % world == rank:
+            img = scenes.render_plane_view(centers[v], Rs[v], f, cx, cy, W, H, extent, tex, dev)
+            t = torch.from_numpy(img).to(dev)
+        else:
+            t = torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
+        if world > 1:
+            dist.broadcast(t, src=v % world)
+        ctx.upload_view(v, P[v], t.cpu().numpy())
+        del t
+    torch.cuda.synchronize()
+    scene_s = time.perf_counter() - t0
+    sc = scenes.Scene("C5", P, [np.zeros((1, 1, 3), np.uint8)] * V, W, H, "plane", extent=extent,
+                      centers=centers)
+    lat = 0.5 * (a.grid - 1) * 4.0
+    sc.extent = lat / 0.8                    # seeds inside the camera lattice
+    seeds = scenes.make_seeds(sc, a.seeds, seed=50, depth_noise=0.003, tilt_deg=5.0)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sync()
+    t0 = time.perf_counter()
+    nvis, vis, _, _ = ctx.visibility(seeds["pos"], seeds["nrm"], seeds["ref"])
+    keep, fnvis, fvis, pos, nrm, evs = ctx.filter_refine(seeds["pos"], seeds["nrm"], seeds["ref"],
+                                                        nvis, vis, 16)
+    m = keep.astype(bool)
+    ctx.organizer_reset()
+    acc = ctx.organizer_insert(pos[m], nrm[m], seeds["ref"][m], fnvis[m], fvis[m])
+    sync()
+    seed_s = time.perf_counter() - t0
+    be = dd.CudaLevelBackend(ctx, dev)
+    tm = {}
+    t0 = time.perf_counter()
+    st = dd.expand_distributed(be, 11, a.levels, rank, world, None, timings=tm, ownership="ranges")
+    sync()
+    exp_s = time.perf_counter() - t0
+    used = free0 - torch.cuda.mem_get_info()[0]
+    ex = ctx.organizer_export()
+    h = hashlib.sha256()
+    for k in ("pos", "nrm", "rgb", "ref", "nvis", "vis"):
+        h.update(np.ascontiguousarray(ex[k]).tobytes())
+    h.update(ctx.organizer_grids().tobytes())
+    digest = h.hexdigest()
+    ok = True
+    L = st["levels"]
+    tv = torch.tensor([tm["local_ms"], tm["allgather_ms"], tm["commit_ms"]], dtype=torch.float64,
+                      device=dev).reshape(3, L)
+    cand = torch.tensor(tm["local_candidates"], dtype=torch.float64, device=dev)
+    if world > 1:
+        hs = [None] * world
+        dist.all_gather_object(hs, digest)
+        ok = all(x == hs[0] for x in hs)
+        dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cand, op=dist.ReduceOp.SUM)
+    rb = ctx.record_bytes()
+    res = dict(config=f"C5 style: {V} views {W}x{H}, {a.seeds} seeds (mu=16 filter + refine), "
+                      f"{a.levels} expansion levels at mu=11", n_gpus=world,
+               image_set_gb=V * H * ((W + 31) // 32 * 32) * 4 / 1e9,
+               mean_visible_views=float(nvis.mean()), seeds_kept=int(m.sum()),
+               seeds_inserted=int(acc.sum()), patches=len(ex["ref"]),
+               candidates_refined=cand.tolist(), level_ms=(tv[0] + tv[1] + tv[2]).tolist(),
+               local_ms=tv[0].tolist(), allgather_ms=tv[1].tolist(), commit_ms=tv[2].tolist(),
+               frontier=tm["frontier"], records_per_level=tm["records"], record_bytes=rb,
+               allgather_bytes_per_level=[int(r) * rb for r in tm["records"]],
+               refined_patches_per_s=float(cand.sum().item()) / (float((tv[0] + tv[1] + tv[2]).sum().item()) * 1e-3),
+               scene_render_broadcast_upload_s=scene_s, seed_stage_s=seed_s, expansion_wall_s=exp_s,
+               device_memory_used_gb=used / 1e9, store_sha256=digest, ranks_equal=bool(ok))
+    if rank == 0:
+        print(json.dumps(res), flush=True)
+        if a.out:
+            json.dump(res, open(a.out, "w"), indent=1)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
