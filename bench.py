@@ -13,7 +13,8 @@ Workload (N=1): BASELINE.json configs[1] -- synthetic textured sphere, 16 views
   value  = patch-view evals/s with the seeds resident in HBM (dp_*_dev entry points)
   e2e    = the same through the host-buffer C ABI (dp_filter_refine on pinned host arrays,
            H2D/D2H inside the timed region)
-  roofline = the refine kernel against the measured HBM copy bandwidth (+ the issue roof)
+  roofline = the refine kernel (dp_refine_lane_kernel) against the measured HBM copy bandwidth
+           (+ the issue roof, from the committed ncu extract while its source hash matches)
   cpu_baseline = the CPU oracle (OpenMP, all host threads) on a bounded sample
 
 Two more legs ride on the same line (both at every N):
@@ -388,7 +389,7 @@ def run_expansion_and_hbm(args, rank, world, local_rank, dev):
         hbm = {"workload": f"{V} views {w_}x{h_} BGRx image set = "
                            f"{V * h_ * ((w_ + 31) // 32 * 32) * 4 / 1e6:.0f} MB (> 126 MB L2), "
                            f"{n} patches per GPU in random order, mu={CELL}",
-               "kernel": "dp_score_group_kernel (all visible views of every patch)",
+               "kernel": "dp_score_lane_kernel<7, 0, 0> (all visible views of every patch)",
                "bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src,
                "mean_visible_views": mean_nv, "alg_bytes_per_eval": b_alg(CELL, mean_nv),
                "achieved": gbs(ev_score, best[0], mean_nv), "frac": gbs(ev_score, best[0], mean_nv) / peak,
@@ -593,7 +594,7 @@ def main():
                 "frac": achieved / peak,
                 "traffic": live["dram_bytes_per_launch"] if live else None,
                 "stale_profile": bool(stale) if cap else None,
-                "kernel": cap["kernel"] if cap else "dp_refine_group_kernel<DpGroupCfg<4, 13, 16, 8>>",
+                "kernel": cap["kernel"] if cap else "dp_refine_lane_kernel<7>",
                 "kernel_ms": refine_kernel_ms, "peak_source": peak_src,
                 "alg_bytes_per_eval": b_alg(CELL, mean_nv), "alg_bytes_per_launch": alg_bytes,
                 "share_of_step": refine_kernel_ms * args.steps / gpu_ms,

@@ -194,9 +194,13 @@ __global__ void dp_u8_to_u32_kernel(const uint8_t *__restrict__ in, unsigned int
 // K5a: which frontier parents expand: >= 2 visible views (expand.cpp:69) and owned by `rank`.
 // Ownership: rank_of_view[reference image] when a table is given; else (world > 1) the frontier
 // is cut into `world` contiguous ranges of equal work -- wscan = exclusive scan of the parents'
-// weights (their visible-view counts, 0 if they do not expand), wtotal its total: parent i
-// belongs to rank floor(wscan[i] * world / wtotal).  Every rank computes the same cut from the
-// replicated store.
+// weights (their visible-view counts, 0 if they do not expand), wtotal its total.  The frontier
+// is cut into world * DP_RANGE_INTERLEAVE pieces of equal work dealt out round-robin (parents
+// that are neighbours in the store are neighbours on the surface and tend to be equally hard, so
+// one long range per rank left the ranks up to 60 % apart; eight interleaved pieces average that
+// out): parent i belongs to rank floor(wscan[i] * world * 8 / wtotal) mod world.  Every rank
+// computes the same cut from the replicated store.
+#define DP_RANGE_INTERLEAVE 8
 __global__ void dp_parent_flags_kernel(const int32_t *__restrict__ nvis,
                                        const int32_t *__restrict__ ref, long long begin,
                                        long long n_f, const int32_t *__restrict__ rank_of_view,
@@ -211,7 +215,8 @@ __global__ void dp_parent_flags_kernel(const int32_t *__restrict__ nvis,
     const int r = ref[p];
     f = (r >= 0 && r < n_views) && rank_of_view[r] == rank;
   } else if (f && wscan) {
-    f = (int)(((unsigned long long)wscan[i] * (unsigned long long)world) / wtotal) == rank;
+    f = (int)((((unsigned long long)wscan[i] * (unsigned long long)(world * DP_RANGE_INTERLEAVE)) / wtotal) %
+              (unsigned long long)world) == rank;
   }
   flags[i] = f ? 1u : 0u;
 }

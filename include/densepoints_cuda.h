@@ -174,8 +174,8 @@ int dp_expand(dp_context *ctx, int cell_size, int max_levels, int64_t *stats);
  * candidate records between steps 1 and 2 with NCCL.
  *  1. dp_expand_level_local : refine + re-derive visibility + filter the children of
  *     the frontier parents this rank owns -- owner = rank_of_view[ref] when a table is given
- *     (n_views entries), or, with rank_of_view == NULL, the rank-th of `world` contiguous
- *     ranges of the frontier with equal work (sum of visible-view counts), the same cut on
+ *     (n_views entries), or, with rank_of_view == NULL, every world-th of 8 * world contiguous
+ *     pieces of the frontier with equal work (sum of visible-view counts), the same cut on
  *     every rank because the store is replicated; survivors are
  *     written as fixed-size records straight into the send buffer `records_dev`
  *     (device pointer, capacity max_records), ascending sequence id;

@@ -42,7 +42,7 @@ class OracleLevelBackend:
         if world > 1 and rov is None:        # equal-work contiguous ranges (dp_parent_flags_kernel)
             w = np.where(st["nvis"][self.begin:] >= 2, st["nvis"][self.begin:], 0).astype(np.int64)
             scan = np.cumsum(w) - w
-            own = (scan * world) // max(int(w.sum()), 1)
+            own = ((scan * world * 8) // max(int(w.sum()), 1)) % world      # DP_RANGE_INTERLEAVE = 8
         for i in range(self.begin, self.org.size()):
             if st["nvis"][i] < 2:
                 continue
