@@ -124,7 +124,7 @@ extern "C" void dp_destroy(dp_context *ctx) {
   DpDevBuf *bufs[] = {&ctx->d_views, &ctx->s_pos, &ctx->s_nrm, &ctx->s_ref, &ctx->s_nvis,
                       &ctx->s_vis, &ctx->s_rgb, &ctx->s_ncc, &ctx->s_tex, &ctx->s_valid,
                       &ctx->s_keep, &ctx->s_evals, &ctx->s_xbest, &ctx->s_cand, &ctx->s_ncand,
-                      &ctx->s_img, &ctx->s_misc, &ctx->work_counter, &ctx->s_order, &ctx->e_pos, &ctx->e_nrm,
+                      &ctx->s_img, &ctx->s_misc, &ctx->work_counter, &ctx->s_order, &ctx->s_nmsave, &ctx->s_pending, &ctx->e_pos, &ctx->e_nrm,
                       &ctx->e_ref, &ctx->e_nvis, &ctx->e_vis, &ctx->e_keep, &ctx->e_seq,
                       &ctx->e_cells, &ctx->e_recs, &ctx->e_flags, &ctx->e_scan, &ctx->e_count, &ctx->org.grid,
                       &ctx->org.claim, &ctx->org.pos, &ctx->org.nrm, &ctx->org.rgb, &ctx->org.ref,
@@ -504,26 +504,90 @@ static cudaError_t launch_refine_wpp(const DpRefineArgs &a, int sm_count, cudaSt
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
   const long long per_cta = DP_RWARPS / WPP;
-  long long want = ((long long)a.p.n + per_cta - 1) / per_cta;
-  long long grid = std::min<long long>(want, (long long)sm_count * per_sm);
+  long long want = ((long long)a.n_items + per_cta - 1) / per_cta;
+  long long grid = std::max<long long>(1, std::min<long long>(want, (long long)sm_count * per_sm));
   dp_refine_kernel<NPASS, WPP><<<(unsigned)grid, DP_RWARPS * 32, 0, st>>>(a);
   return cudaGetLastError();
 }
-// Batches that cannot keep the machine busy for long with one warp per patch run four warps,
-// or a whole CTA of eight, per patch (visible sets up to DP_MW_MAXV views): such a launch lasts
-// about as long as its longest patch -- up to 500 dependent evaluations -- and k warps shorten
-// that latency almost k-fold.  Measured on the 64-view expansion (bench.py, 8 GPUs): levels with
-// ~5 000 candidates per GPU took 10-12 ms with one warp per patch whatever their size, the
-// levels below 2 400 candidates 2-4 ms with four.  DP_REFINE_WPP=1 forces one warp per patch.
+static long long env_ll(const char *name, long long dflt) {
+  const char *e = getenv(name);
+  return e ? atoll(e) : dflt;
+}
+// Warp-per-patch refinement (cells > 8), TIME-SLICED.  A launch of persistent warps lasts at
+// least as long as its longest patch -- up to 500 dependent evaluations of up to ~50 views, 10-12
+// ms with one warp per patch -- however few patches it has: measured on the 64-view expansion
+// split over 8 GPUs (tools/shard_balance.py), levels whose ideal share was 2-8 ms took 4-14 ms.
+// So a launch gives every patch a budget of evaluations; a patch that needs more is stopped with
+// its Nelder-Mead state saved bit for bit (DpRefineArgs::nm_save) and continues in the next
+// launch -- and the fewer patches are left, the more warps each one gets (four, then the whole
+// CTA of eight: the views of a patch are dealt out to the warps, which shortens the dependent
+// chain almost k-fold).  The stopped-and-resumed trajectory is the uninterrupted one, so every
+// output is unchanged.  Between launches the host reads one counter (the stream is synchronised;
+// the callers of this path -- the expansion levels -- synchronise anyway).
+// Measured (tools/shard_balance.py, B200, the 12 levels of bench.py's 64-view expansion; budgets
+// 128 / 256 evaluations for the one- / four-warp launches, thresholds 64 and 4 patches per SM):
+// one GPU 705 -> 643 ms (a stopped patch restarts at the head of the next launch, which is the
+// longest-first order the view count alone cannot give), slowest of 8 shards per level, summed,
+// 126 -> 110 ms.  DP_SLICE_B1 / _B4 / _T4 / _T8 override the knobs, DP_REFINE_SLICE=0 disables.
+// DP_REFINE_WPP=1 forces one unsliced launch with one warp per patch (A-B runs).
 template <int NPASS>
-static cudaError_t launch_refine(const DpRefineArgs &a, int sm_count, cudaStream_t st) {
+static int refine_sliced(dp_context *ctx, DpRefineArgs a, const int32_t *nvis, cudaStream_t st) {
+  const long long n = a.p.n;
   const char *e = getenv("DP_REFINE_WPP");
   const bool allow_mw = !(e && atoi(e) == 1) && a.p.vstride <= DP_MW_MAXV;
-  if (allow_mw && (long long)a.p.n <= (long long)sm_count * 4)
-    return launch_refine_wpp<NPASS, 8>(a, sm_count, st);
-  if (allow_mw && (long long)a.p.n <= (long long)sm_count * 64)
-    return launch_refine_wpp<NPASS, 4>(a, sm_count, st);
-  return launch_refine_wpp<NPASS, 1>(a, sm_count, st);
+  const long long t8 = env_ll("DP_SLICE_T8", (long long)ctx->sm_count * 4);
+  const long long t4 = env_ll("DP_SLICE_T4", (long long)ctx->sm_count * 64);
+  const int b1 = (int)env_ll("DP_SLICE_B1", 128), b4 = (int)env_ll("DP_SLICE_B4", 256);
+  const bool slice = allow_mw && env_ll("DP_REFINE_SLICE", 1) != 0 && n > t8;
+  a.n_items = (unsigned int)n;
+  a.nm_save = nullptr;
+  a.pending = nullptr;
+  a.pending_count = nullptr;
+  a.budget = 0;
+  a.resume = 0;
+  if (!slice) {
+    cudaError_t ce;
+    if (allow_mw && n <= t8) ce = launch_refine_wpp<NPASS, 8>(a, ctx->sm_count, st);
+    else if (allow_mw && n <= t4) ce = launch_refine_wpp<NPASS, 4>(a, ctx->sm_count, st);
+    else ce = launch_refine_wpp<NPASS, 1>(a, ctx->sm_count, st);
+    ++ctx->launches;
+    DP_CUDA(ctx, ce);
+    return DP_OK;
+  }
+  DP_CUDA(ctx, ctx->s_nmsave.ensure((size_t)n * DP_NM_SAVE_WORDS * sizeof(double)));
+  DP_CUDA(ctx, ctx->s_pending.ensure((size_t)n + 16));
+  a.nm_save = ctx->s_nmsave.as<double>();
+  a.pending = ctx->s_pending.as<uint8_t>();
+  // the counter sits behind the flags, 8-byte aligned
+  a.pending_count = reinterpret_cast<unsigned int *>(a.pending + (((size_t)n + 7) & ~(size_t)7));
+  long long m = n;
+  for (int phase = 0;; ++phase) {
+    int wpp = 1;
+    a.budget = b1;
+    if (m <= t8) { wpp = 8; a.budget = 0; }
+    else if (m <= t4) { wpp = 4; a.budget = b4; }
+    DP_CUDA(ctx, cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned int), st));
+    DP_CUDA(ctx, cudaMemsetAsync(a.pending_count, 0, sizeof(unsigned int), st));
+    cudaError_t ce;
+    if (wpp == 8) ce = launch_refine_wpp<NPASS, 8>(a, ctx->sm_count, st);
+    else if (wpp == 4) ce = launch_refine_wpp<NPASS, 4>(a, ctx->sm_count, st);
+    else ce = launch_refine_wpp<NPASS, 1>(a, ctx->sm_count, st);
+    ++ctx->launches;
+    DP_CUDA(ctx, ce);
+    if (a.budget == 0) break;
+    unsigned int left = 0;
+    DP_CUDA(ctx, cudaMemcpyAsync(&left, a.pending_count, sizeof(left), cudaMemcpyDeviceToHost, st));
+    DP_CUDA(ctx, cudaStreamSynchronize(st));
+    if (left == 0) break;
+    m = left;
+    // the stopped patches (all have >= 2 views) sort in front of the finished ones (key 0)
+    a.mask = a.pending;
+    a.resume = 1;
+    int rc = build_order(ctx, nvis, a.pending, (int)n, st, &a.order);
+    if (rc != DP_OK) return rc;
+    a.n_items = a.order ? (unsigned int)m : (unsigned int)n;
+  }
+  return DP_OK;
 }
 
 #ifndef DP_REFINE_GROUP
@@ -590,6 +654,12 @@ extern "C" int dp_refine_dev(dp_context *ctx, dp_patch_dev *p, int cell_size, co
   a.eps = ctx->prm.nm_eps;
   a.work_counter = ctx->work_counter.as<unsigned int>();
   a.mask = mask;
+  a.n_items = (unsigned int)p->n;
+  a.nm_save = nullptr;
+  a.pending = nullptr;
+  a.pending_count = nullptr;
+  a.budget = 0;
+  a.resume = 0;
 #ifdef DP_DEBUG_TRACE
   {
     static double *tr = nullptr;
@@ -623,13 +693,18 @@ extern "C" int dp_refine_dev(dp_context *ctx, dp_patch_dev *p, int cell_size, co
     }
 #undef DP_GCASE
   } else
-  switch (npass_for(cell_size)) {
-    case 1: e = launch_refine<1>(a, ctx->sm_count, st); break;
-    case 2: e = launch_refine<2>(a, ctx->sm_count, st); break;
-    case 4: e = launch_refine<4>(a, ctx->sm_count, st); break;
-    case 8: e = launch_refine<8>(a, ctx->sm_count, st); break;
-    case 16: e = launch_refine<16>(a, ctx->sm_count, st); break;
-    default: e = launch_refine<32>(a, ctx->sm_count, st); break;
+  {
+    e = cudaSuccess;
+    --ctx->launches;  // refine_sliced counts its own launches
+    switch (npass_for(cell_size)) {
+      case 1: rc = refine_sliced<1>(ctx, a, p->nvis, st); break;
+      case 2: rc = refine_sliced<2>(ctx, a, p->nvis, st); break;
+      case 4: rc = refine_sliced<4>(ctx, a, p->nvis, st); break;
+      case 8: rc = refine_sliced<8>(ctx, a, p->nvis, st); break;
+      case 16: rc = refine_sliced<16>(ctx, a, p->nvis, st); break;
+      default: rc = refine_sliced<32>(ctx, a, p->nvis, st); break;
+    }
+    if (rc != DP_OK) return rc;
   }
   ++ctx->launches;
   DP_CUDA(ctx, e);

@@ -91,6 +91,7 @@ struct dp_context {
   DpDevBuf s_pos, s_nrm, s_ref, s_nvis, s_vis, s_rgb, s_ncc, s_tex, s_valid, s_keep, s_evals,
       s_xbest, s_cand, s_ncand, s_img, s_misc;
   DpDevBuf work_counter, s_order;
+  DpDevBuf s_nmsave, s_pending;  // time-sliced refinement: stopped patches' solver state, flags
   // The dp_*_dev calls share the scratch above and below (work counter, order table, expansion
   // buffers).  Calls on different streams are therefore chained: a call first makes its stream
   // wait for the event the previous call recorded on its own stream (dp_scratch_acquire /

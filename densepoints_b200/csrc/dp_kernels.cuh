@@ -229,6 +229,16 @@ struct DpRefineArgs {
   unsigned int *work_counter;  // zeroed before launch
   const uint8_t *mask;         // optional: refine only patches with mask[i] != 0
   const int32_t *order;        // optional: work item k = patch order[k] (longest-first schedule)
+  // Time slicing (dp_refine_kernel; see refine_sliced in densepoints_cuda.cu): a launch stops a
+  // patch after `budget` objective evaluations and saves its Nelder-Mead state bit for bit; a
+  // later launch with resume = 1 (and mask = pending) picks it up where it stopped, so the
+  // trajectory -- and every output -- is the one of an uninterrupted run.
+  double *nm_save;             // n * DP_NM_SAVE_WORDS doubles, or null (no slicing)
+  uint8_t *pending;            // n flags, written by every launch: 1 = stopped, to be continued
+  unsigned int *pending_count; // number of patches this launch left pending (zeroed before)
+  int budget;                  // evaluations per patch in this launch; 0 = unlimited
+  int resume;                  // 1: the patches with mask != 0 continue from nm_save
+  unsigned int n_items;        // work items dp_refine_kernel hands out (<= n; the first entries of order)
 #ifdef DP_DEBUG_TRACE
   double *trace;               // debug builds: objective value of the first 8 evaluations, n*8
 #endif
@@ -314,6 +324,10 @@ struct DpNelderMead {
   double n0[3], p0[3], c3[3];  // patch normal / position at entry, reference camera centre
   double y_alpha, y_lo, y_nhi, y_hi;
 };
+
+// A stopped patch in global memory: the DpNelderMead words, then (state, idx, fcount, ilo, ihi).
+#define DP_NM_STRUCT_WORDS ((int)(sizeof(DpNelderMead) / sizeof(double)))
+#define DP_NM_SAVE_WORDS (DP_NM_STRUCT_WORDS + 5)
 
 __device__ __forceinline__ void nm_store3(double *dst, const double v[3], int lane) {
   __syncwarp();
@@ -405,10 +419,13 @@ __global__ void __launch_bounds__(DP_RWARPS * 32, dp_refine_min_ctas(NPASS)) dp_
       iu = gitem[grp];
       dp_group_barrier(1 + grp, WPP * 32);
     }
-    if (iu >= (unsigned int)a.p.n) break;
+    if (iu >= a.n_items) break;
     const long long i = a.order ? (long long)a.order[iu] : (long long)iu;
     if (a.mask != nullptr && a.mask[i] == 0) {  // removed by Seed::RemovePatches (seed.cpp:146-156)
-      if (a.evals && lane == 0 && wg == 0) a.evals[i] = 0;
+      if (!a.resume && lane == 0 && wg == 0) {  // (resume: finished in an earlier launch)
+        if (a.evals) a.evals[i] = 0;
+        if (a.pending) a.pending[i] = 0;
+      }
       continue;
     }
     const int nv = min(a.p.nvis[i], a.p.vstride);
@@ -440,8 +457,40 @@ __global__ void __launch_bounds__(DP_RWARPS * 32, dp_refine_min_ctas(NPASS)) dp_
     __syncwarp();
     int state = ST_INIT, idx = 0, fcount = 4;
     int ilo = 0, ihi = 0;
+    if (a.resume) {  // continue a stopped patch: every warp of the group loads the same state
+      const double *sv = a.nm_save + (size_t)i * DP_NM_SAVE_WORDS;
+      double *Sd = reinterpret_cast<double *>(&S);
+      for (int t = lane; t < DP_NM_STRUCT_WORDS; t += 32) Sd[t] = sv[t];
+      state = (int)sv[DP_NM_STRUCT_WORDS];
+      idx = (int)sv[DP_NM_STRUCT_WORDS + 1];
+      fcount = (int)sv[DP_NM_STRUCT_WORDS + 2];
+      ilo = (int)sv[DP_NM_STRUCT_WORDS + 3];
+      ihi = (int)sv[DP_NM_STRUCT_WORDS + 4];
+      __syncwarp();
+    }
+    int spent = 0;  // objective evaluations of this patch in this launch
 #pragma unroll 1
     for (;;) {
+      if (a.budget > 0 && spent >= a.budget && state != ST_DONE) {
+        // out of budget: the state goes to global memory as it is, S.pt is the next point
+        __syncwarp();
+        if (wg == 0) {
+          double *sv = a.nm_save + (size_t)i * DP_NM_SAVE_WORDS;
+          const double *Sd = reinterpret_cast<const double *>(&S);
+          for (int t = lane; t < DP_NM_STRUCT_WORDS; t += 32) sv[t] = Sd[t];
+          if (lane == 0) {
+            sv[DP_NM_STRUCT_WORDS] = (double)state;
+            sv[DP_NM_STRUCT_WORDS + 1] = (double)idx;
+            sv[DP_NM_STRUCT_WORDS + 2] = (double)fcount;
+            sv[DP_NM_STRUCT_WORDS + 3] = (double)ilo;
+            sv[DP_NM_STRUCT_WORDS + 4] = (double)ihi;
+            a.pending[i] = 1;
+            atomicAdd(a.pending_count, 1u);
+          }
+        }
+        break;
+      }
+      ++spent;
       // UnparametrizePatch at the point to evaluate (or, in ST_DONE, at the best vertex)
       double n[3], p[3];
       const double p0[3] = {S.p0[0], S.p0[1], S.p0[2]};  // GetPosition(): the corner centre
@@ -461,7 +510,10 @@ __global__ void __launch_bounds__(DP_RWARPS * 32, dp_refine_min_ctas(NPASS)) dp_
           }
           if (a.xbest) a.xbest[3 * i + lane] = S.pt[lane];
         }
-        if (a.evals && lane == 0 && wg == 0) a.evals[i] = fcount;
+        if (lane == 0 && wg == 0) {
+          if (a.evals) a.evals[i] = fcount;
+          if (a.pending) a.pending[i] = 0;
+        }
         break;
       }
       // ---- the single objective call site: PatchOptimizationOpenCVFunctor::calc ----------

@@ -219,6 +219,10 @@ int dp_score_dev(dp_context *ctx, const dp_patch_dev *p, int cell_size, float *n
 int dp_score_at_dev(dp_context *ctx, const dp_patch_dev *p, int cell_size, const double *normal,
                     const double *position, float *ncc, uint8_t *tex, uint8_t *valid, void *stream);
 int dp_filter_dev(dp_context *ctx, dp_patch_dev *p, int cell_size, uint8_t *keep, void *stream);
+/* dp_refine_dev with cell_size > 8 and more than 4 patches per SM runs time-sliced (several
+ * launches with an evaluation budget, the Nelder-Mead state of unfinished patches carried over
+ * bit for bit): it reads one counter between launches, i.e. it synchronises `stream` and returns
+ * with at most the last launch in flight.  Results do not depend on the slicing. */
 int dp_refine_dev(dp_context *ctx, dp_patch_dev *p, int cell_size, const uint8_t *mask,
                   int32_t *evals, double *xbest, void *stream);
 int dp_visibility_dev(dp_context *ctx, dp_patch_dev *p, int32_t *ncand, int32_t *cand,

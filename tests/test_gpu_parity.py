@@ -194,6 +194,45 @@ def test_refine_vs_oracle(c1, exact_orc, s, n, refine_kernel):
     assert evals.min() >= 4 and evals.max() <= 503
 
 
+@pytest.mark.parametrize("s,knobs", [
+    (11, dict(DP_SLICE_T8="10", DP_SLICE_T4="100", DP_SLICE_B1="7", DP_SLICE_B4="9")),   # 1 -> 4 -> 8 warps
+    (11, dict(DP_SLICE_T8="1", DP_SLICE_T4="1", DP_SLICE_B1="5")),                       # many 1-warp slices
+    (16, dict(DP_SLICE_T8="1", DP_SLICE_T4="100000", DP_SLICE_B4="6")),                  # 4-warp slices only
+    (20, dict(DP_SLICE_T8="200", DP_SLICE_T4="300", DP_SLICE_B1="16", DP_SLICE_B4="16")),
+])
+def test_time_sliced_refine_is_the_uninterrupted_run(c1, exact_orc, monkeypatch, s, knobs):
+    """Cells > 8: dp_refine_dev cuts the Nelder-Mead runs of a batch into launches with an
+    evaluation budget, saving and restoring the solver state (refine_sliced,
+    densepoints_cuda.cu), with more warps per patch as fewer patches are left.  Whatever the
+    budgets and thresholds, the result must be the unsliced one bit for bit -- and the
+    oracle's (optimization_opencv.cpp:44-78)."""
+    d = c1
+    sd = d["seeds"]
+    n = 1200
+    sl = slice(0, n)
+    args = (sd["pos"][sl], sd["nrm"][sl], sd["ref"][sl], d["nvis"][sl], d["vis"][sl], s)
+    monkeypatch.setenv("DP_REFINE_SLICE", "0")
+    p0, n0, e0, x0 = d["ctx"].refine(*args)
+    monkeypatch.setenv("DP_REFINE_SLICE", "1")
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    l0 = d["ctx"].launch_count()
+    p1, n1, e1, x1 = d["ctx"].refine(*args)
+    assert d["ctx"].launch_count() - l0 >= 3              # it did run in several slices
+    assert np.array_equal(e0, e1) and np.array_equal(x0, x1)
+    assert np.array_equal(p0, p1) and np.array_equal(n0, n1)
+    m = 150                                               # and both equal the oracle
+    o_pos, o_nrm, o_fc, o_xb = exact_orc.refine_batch(d["V"], *[a[:m] for a in args[:5]], s)
+    assert np.array_equal(e1[:m], o_fc) and np.array_equal(p1[:m], o_pos) and np.array_equal(n1[:m], o_nrm)
+    # a mask (Seed::RemovePatches) in the first slice, then resumed slices
+    mask = (np.arange(n) % 3 != 0).astype(np.uint8)
+    p2, n2, e2, _ = d["ctx"].refine(*args, mask=mask)
+    mb = mask.astype(bool)
+    assert np.array_equal(e2[mb], e0[mb]) and (e2[~mb] == 0).all()
+    assert np.array_equal(p2[mb], p0[mb]) and np.array_equal(n2[mb], n0[mb])
+    assert np.array_equal(p2[~mb], sd["pos"][sl][~mb]) and np.array_equal(n2[~mb], sd["nrm"][sl][~mb])
+
+
 @pytest.mark.parametrize("s", [2, 3, 4, 6, 8])
 def test_group_kernels_every_small_cell(c1, exact_orc, s, refine_kernel):
     """Cells up to 8x8 run the several-patches-per-warp kernels (dp_group.cuh), one template
