@@ -281,9 +281,13 @@ def run_expansion_and_hbm(args, rank, world, local_rank, dev):
         tm = {}
         sync()
         t1 = time.perf_counter()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
         st = dd.expand_distributed(be, EXP_CELL, EXP_MAX_LEVELS, rank, world, None, timings=tm,
                                    ownership=ownership)
+        ev1.record()
         sync()
+        tm["device_ms"] = ev0.elapsed_time(ev1)          # the whole expansion on this rank's stream
         return st, tm, time.perf_counter() - t1, int(acc.sum())
 
     # for the record: strict ownership by reference image (re-balanced per level); its speed-up is
@@ -298,7 +302,10 @@ def run_expansion_and_hbm(args, rank, world, local_rank, dev):
         lmin_v = tv_v[0].clone()
         dist.all_reduce(tv_v, op=dist.ReduceOp.MAX)
         dist.all_reduce(lmin_v, op=dist.ReduceOp.MIN)
-        by_view = {"expansion_ms": float((tv_v[0] + tv_v[1] + tv_v[2]).sum().item()),
+        dv_v = torch.tensor([tm_v["device_ms"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(dv_v, op=dist.ReduceOp.MAX)
+        by_view = {"expansion_ms": float(dv_v.item()),
+                   "sum_of_phase_maxima_ms": float((tv_v[0] + tv_v[1] + tv_v[2]).sum().item()),
                    "local_ms_max_rank": tv_v[0].tolist(), "local_ms_min_rank": lmin_v.tolist(),
                    "store_sha256": dg_v}
     one_run()                                            # warm-up (allocations, NCCL channels)
@@ -310,7 +317,7 @@ def run_expansion_and_hbm(args, rank, world, local_rank, dev):
                       device=dev).reshape(3, L)
     tmin = tv[0].clone()
     cand = torch.tensor(tm["local_candidates"], dtype=torch.float64, device=dev)
-    wall = torch.tensor([wall_s], dtype=torch.float64, device=dev)
+    wall = torch.tensor([wall_s, tm["device_ms"]], dtype=torch.float64, device=dev)
     ok = torch.ones(1, dtype=torch.int32, device=dev)
     if world > 1:
         dist.all_reduce(tv, op=dist.ReduceOp.MAX)
@@ -321,21 +328,28 @@ def run_expansion_and_hbm(args, rank, world, local_rank, dev):
         dist.all_gather_object(hs, digest)
         ok[0] = 1 if all(h == hs[0] for h in hs) else 0
     level_ms = (tv[0] + tv[1] + tv[2]).tolist()
-    total_ms = float(sum(level_ms))
+    # the expansion's time: CUDA events around the whole level loop on each rank's stream (after a
+    # barrier + synchronize), max over ranks.  (The per-level phase times below are maxima over
+    # ranks phase by phase -- a rank that waits in the allgather for a slower one is counted
+    # there AND in the slower rank's local step -- so their sum overstates the run.)
+    total_ms = float(wall[1].item())
     cand_total = float(cand.sum().item())
     exp = {"workload": f"BASELINE configs[3] style: {nv_} views {w_}x{h_} plane scene, {n_seeds} seeds "
                        f"(mu={EXP_SEED_CELL} filter + refine), Expand::ExpandPatches at mu={EXP_CELL}, "
                        f"level cap {EXP_MAX_LEVELS}",
            "scaling": "strong", "n_gpus": world,
-           "sharding": "the frontier's parents in N contiguous ranges of equal work (sum of visible-view "
-                       "counts), cut identically on every rank from the replicated store; one NCCL "
-                       "allgather of candidate records per level",
+           "sharding": "the frontier's parents in 8 N contiguous pieces of equal work (sum of visible-view "
+                       "counts) dealt out round-robin, cut identically on every rank from the replicated "
+                       "store; one NCCL allgather of candidate records per level",
            "by_reference_image": by_view,
            "levels": L, "seeds_kept": int(m.sum()), "seeds_inserted": seeded,
            "patches": n_store, "candidates_refined": int(cand_total), "records_gathered": st["passed"],
            "inserted": st["inserted"], "record_bytes": ctx.record_bytes(),
            "refined_patches_per_s": cand_total / (total_ms * 1e-3) if total_ms > 0 else None,
-           "expansion_ms": total_ms, "wall_ms": float(wall.item()) * 1e3,
+           "expansion_ms": total_ms, "wall_ms": float(wall[0].item()) * 1e3,
+           "sum_of_phase_maxima_ms": float(sum(level_ms)),
+           "timing": "expansion_ms = CUDA events around the whole level loop, max over ranks; "
+                     "level_ms / local_ms / allgather_ms / commit_ms = per-level maxima over ranks",
            "level_ms": level_ms, "local_ms": tv[0].tolist(), "local_ms_min_rank": tmin.tolist(),
            "allgather_ms": tv[1].tolist(), "commit_ms": tv[2].tolist(),
            "frontier": tm["frontier"], "records_per_level": tm["records"],

@@ -37,23 +37,33 @@
 #define DP_LTSTR (DP_LTILE + 4)   // tile stride between lanes: 16-byte aligned, staggers the banks
 #define DP_LGROUP_MAX_CELL 8
 #define DP_NM_WORDS 23    // P[4][3], y[4], pt[3], pa[3], y_alpha
+#ifndef DP_LANE_NM_LOCAL
+#define DP_LANE_NM_LOCAL 0  // 1: the Nelder-Mead words live in (L1-cached) local memory
+#endif
+#if DP_LANE_NM_LOCAL
+#define DP_NM_STRIDE 1
+#else
+#define DP_NM_STRIDE 32
+#endif
 
 template <int S>
 struct DpLaneShared {
   // +32 words: the neighbour taps of an edge pixel (weight 0) may read past the last tile
   __align__(16) uint32_t tile[DP_LWARPS][32 * DP_LTSTR + 32];
   uint2 gray[DP_LWARPS][2][S][32];          // [0] anchor texture, [1] current view: a row of bytes
+#if !DP_LANE_NM_LOCAL
   double nm[DP_LWARPS][DP_NM_WORDS][32];
+#endif
 };
 
 // Nelder-Mead state of the lane's patch: word k at b[32 k] (shared memory, [word][lane]).
 struct DpNmLane {
   double *b;
-  __device__ __forceinline__ double &P(int v, int j) const { return b[32 * (3 * v + j)]; }
-  __device__ __forceinline__ double &y(int v) const { return b[32 * (12 + v)]; }
-  __device__ __forceinline__ double &pt(int j) const { return b[32 * (16 + j)]; }
-  __device__ __forceinline__ double &pa(int j) const { return b[32 * (19 + j)]; }
-  __device__ __forceinline__ double &y_alpha() const { return b[32 * 22]; }
+  __device__ __forceinline__ double &P(int v, int j) const { return b[DP_NM_STRIDE * (3 * v + j)]; }
+  __device__ __forceinline__ double &y(int v) const { return b[DP_NM_STRIDE * (12 + v)]; }
+  __device__ __forceinline__ double &pt(int j) const { return b[DP_NM_STRIDE * (16 + j)]; }
+  __device__ __forceinline__ double &pa(int j) const { return b[DP_NM_STRIDE * (19 + j)]; }
+  __device__ __forceinline__ double &y_alpha() const { return b[DP_NM_STRIDE * 22]; }
 };
 
 // tryNewPoint: ptry = coord_sum * (1-a)/n - p_hi * ((1-a)/n - a) -> pt; coord_sum is the sum of
@@ -522,11 +532,16 @@ __global__ void __launch_bounds__(DP_LWARPS * 32, DP_LMINCTA) dp_refine_lane_ker
   constexpr int npx = S * S;
   const double scale = 1.0 / (double)npx;  // cv::meanStdDev: mean = sum * (1/N)
   const double inv_s = 1.0 / (double)S;
+#if DP_LANE_NM_LOCAL
+  double nm_words[DP_NM_WORDS];
+  const DpNmLane NM{nm_words};
+#else
   const DpNmLane NM{&sh.nm[warp][0][lane]};
+#endif
   uint32_t *warp_tiles = sh.tile[warp];
   uint2 *gA = &sh.gray[warp][0][0][lane], *gB = &sh.gray[warp][1][0][lane];
 #pragma unroll 1
-  for (int k = 0; k < DP_NM_WORDS; ++k) NM.b[32 * k] = 0.0;  // defined values for idle lanes
+  for (int k = 0; k < DP_NM_WORDS; ++k) NM.b[DP_NM_STRIDE * k] = 0.0;  // defined values for idle lanes
   bool have = false, exhausted = false;
   long long i = 0;
   int nv = 0, ref = 0;
