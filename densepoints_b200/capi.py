@@ -426,6 +426,11 @@ class Context:
     def set_level(self, level):
         self._ck(lib().dp_set_level(self._h, C.c_int(level)), "dp_set_level")
 
+    def set_level_selection(self, enable, px_per_cell=1.5):
+        """Per-(patch, view) pyramid level (dp_set_level_selection)."""
+        self._ck(lib().dp_set_level_selection(self._h, C.c_int(1 if enable else 0),
+                                              C.c_double(px_per_cell)), "dp_set_level_selection")
+
     def download_level(self, view, level):
         w, h = C.c_int(0), C.c_int(0)
         self._ck(lib().dp_download_level(self._h, C.c_int(view), C.c_int(level), None,

@@ -124,7 +124,7 @@ extern "C" void dp_destroy(dp_context *ctx) {
   DpDevBuf *bufs[] = {&ctx->d_views, &ctx->s_pos, &ctx->s_nrm, &ctx->s_ref, &ctx->s_nvis,
                       &ctx->s_vis, &ctx->s_rgb, &ctx->s_ncc, &ctx->s_tex, &ctx->s_valid,
                       &ctx->s_keep, &ctx->s_evals, &ctx->s_xbest, &ctx->s_cand, &ctx->s_ncand,
-                      &ctx->s_img, &ctx->s_misc, &ctx->work_counter, &ctx->s_order, &ctx->s_nmsave, &ctx->s_pending, &ctx->e_pos, &ctx->e_nrm,
+                      &ctx->s_img, &ctx->s_misc, &ctx->work_counter, &ctx->s_order, &ctx->d_views_lv, &ctx->s_nmsave, &ctx->s_pending, &ctx->e_pos, &ctx->e_nrm,
                       &ctx->e_ref, &ctx->e_nvis, &ctx->e_vis, &ctx->e_keep, &ctx->e_seq,
                       &ctx->e_cells, &ctx->e_recs, &ctx->e_flags, &ctx->e_scan, &ctx->e_count, &ctx->org.grid,
                       &ctx->org.claim, &ctx->org.pos, &ctx->org.nrm, &ctx->org.rgb, &ctx->org.ref,
@@ -284,33 +284,42 @@ int dp_sync_views(dp_context *ctx) {
   if (!ctx->views_dirty) return DP_OK;
   const int nv = (int)ctx->views.size();
   if (nv == 0) return dp_fail(ctx, DP_ERR_STATE, "no views uploaded");
-  std::vector<DpViewDev> h(nv);
+  const int n_tab = ctx->auto_level ? ctx->n_levels - ctx->level : 1;  // base level + the ones above
+  std::vector<DpViewDev> h((size_t)nv * n_tab);
   long long off = 0;
   for (int i = 0; i < nv; ++i) {
     const DpViewHost &v = ctx->views[i];
     if (!v.set) return dp_fail(ctx, DP_ERR_STATE, "a view was not uploaded");
-    if (ctx->level >= (int)v.levels.size())
+    if (ctx->level + n_tab > (int)v.levels.size())
       return dp_fail(ctx, DP_ERR_STATE, "pyramid level not built");
-    const DpLevel &l = v.levels[ctx->level];
-    const double sc = ldexp(1.0, -ctx->level);
-    for (int j = 0; j < 12; ++j) h[i].P[j] = (j < 8) ? v.P[j] * sc : v.P[j];
     const double n = sqrt(v.xaxis[0] * v.xaxis[0] + v.xaxis[1] * v.xaxis[1] + v.xaxis[2] * v.xaxis[2]);
-    for (int j = 0; j < 3; ++j) {
-      h[i].xa[j] = v.xaxis[j] / n;  // .normalized(), patch.cpp:95
-      h[i].center[j] = v.center[j];
-    }
-    h[i].img = l.img;
-    h[i].width = l.width;
-    h[i].height = l.height;
-    h[i].pitch_px = l.pitch_px;
-    h[i].gw = l.width / ctx->prm.grid_scale;   // patch_organizer.cpp:35-36
-    h[i].gh = l.height / ctx->prm.grid_scale;
-    h[i].grid_off = off;
+    for (int t = 0; t < n_tab; ++t) {
+      DpViewDev &d = h[(size_t)t * nv + i];
+      const DpLevel &l = v.levels[ctx->level + t];
+      const double sc = ldexp(1.0, -(ctx->level + t));
+      for (int j = 0; j < 12; ++j) d.P[j] = (j < 8) ? v.P[j] * sc : v.P[j];
+      for (int j = 0; j < 3; ++j) {
+        d.xa[j] = v.xaxis[j] / n;  // .normalized(), patch.cpp:95
+        d.center[j] = v.center[j];
+      }
+      d.img = l.img;
+      d.width = l.width;
+      d.height = l.height;
+      d.pitch_px = l.pitch_px;
+      d.gw = l.width / ctx->prm.grid_scale;   // patch_organizer.cpp:35-36
+      d.gh = l.height / ctx->prm.grid_scale;
+      d.grid_off = off;   // (the grids belong to the base level; the tables above it are only
+    }                     //  read for their image and projection)
     off += (long long)h[i].gw * h[i].gh;
   }
   DP_CUDA(ctx, ctx->d_views.ensure(sizeof(DpViewDev) * nv));
   DP_CUDA(ctx, cudaMemcpyAsync(ctx->d_views.ptr, h.data(), sizeof(DpViewDev) * nv,
                                cudaMemcpyHostToDevice, ctx->stream));
+  if (n_tab > 1) {
+    DP_CUDA(ctx, ctx->d_views_lv.ensure(sizeof(DpViewDev) * h.size()));
+    DP_CUDA(ctx, cudaMemcpyAsync(ctx->d_views_lv.ptr, h.data(), sizeof(DpViewDev) * h.size(),
+                                 cudaMemcpyHostToDevice, ctx->stream));
+  }
   DP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->org.n_cells = off;
   ctx->views_dirty = false;
@@ -348,6 +357,12 @@ static DpPatchArgs patch_args(dp_context *ctx, const dp_patch_dev *p, int s) {
   a.nvis = p->nvis;
   a.vis = p->vis;
   a.s = s;
+  // per-(patch, view) level: only when levels above the base exist
+  const int up = ctx->auto_level ? ctx->n_levels - 1 - ctx->level : 0;
+  a.lv.tab = up > 0 ? ctx->d_views_lv.as<DpViewDev>() : nullptr;
+  a.lv.up = up;
+  const double side = ctx->level_px * (double)s;
+  a.lv.thr2 = side * side;
   return a;
 }
 

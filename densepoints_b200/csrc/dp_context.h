@@ -85,6 +85,9 @@ struct dp_context {
   bool views_dirty = true;
   int level = 0;
   int n_levels = 1;
+  bool auto_level = false;       // dp_set_level_selection: per-(patch, view) pyramid level
+  double level_px = 1.5;         // ... a texel may cover this many pixels of the level it is read from
+  DpDevBuf d_views_lv;           // DpViewDev[n_levels - level][n_views]: the base level and the ones above
   std::string err;
   int64_t launches = 0;
   // scratch for the host-buffer API

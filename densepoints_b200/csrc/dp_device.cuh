@@ -32,6 +32,15 @@ struct DpViewDev {
 
 #define DP_FULL 0xffffffffu
 
+// Per-(patch, view) pyramid level (dp_set_level_selection).  tab = the view tables
+// of the base level (index 0 = the table the kernels get as `views`) and of the `up` coarser
+// levels above it, [up + 1][n_views]; null = every view is read at the base level.
+struct DpLevelSel {
+  const DpViewDev *tab;
+  int up;
+  double thr2;  // (px_per_cell * s)^2: squared side of the projected quad beyond which the next level is used
+};
+
 // fp64 operations that must not be contracted into FMAs: the set-up chain
 // (axes -> corners -> projection -> fp32 points -> ROI) mirrors the reference's
 // unfused evaluation order so the fp32-rounded quad and the integer ROI agree.
@@ -74,6 +83,24 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(DP_FULL, v, o);
   return v;
+}
+
+// How many levels above the base a view is read at: the longer of the two quad sides through
+// corner 0, in base-level pixels, is halved until it is shorter than px_per_cell * s (so a texel
+// of the s x s cell covers less than px_per_cell pixels of the level it is sampled from).
+// (du1, dv1) = corner 1 - corner 0, (du3, dv3) = corner 3 - corner 0.  NaN sides pick level 0.
+__device__ __forceinline__ int dp_pick_level(double du1, double dv1, double du3, double dv3,
+                                             double thr2, int up) {
+  const double a = xadd(xmul(du1, du1), xmul(dv1, dv1));
+  const double b = xadd(xmul(du3, du3), xmul(dv3, dv3));
+  const double d2 = (b > a) ? b : a;
+  int k = 0;
+  double t = thr2;
+  while (k < up && d2 >= t) {
+    ++k;
+    t = xmul(t, 4.0);
+  }
+  return k;
 }
 
 // Per-patch frame: scaled patch axes in world units (optimization.cpp:19-30).
@@ -238,7 +265,7 @@ __device__ __forceinline__ bool dp_quad_map(double qx0, double qy0, double qx1, 
 // bound must be warp-uniform: the shuffles below are full-warp).
 template <int GL = 32, typename REC = DpViewSetup>
 __device__ __forceinline__ void dp_setup_views(const DpViewDev *__restrict__ views, int n_views,
-                                               const int32_t *vis, int kcount, int kcmax, int s,
+                                               const DpLevelSel &lv, const int32_t *vis, int kcount, int kcmax, int s,
                                                const DpFrame &f, REC *recs, int lane) {
   const int c = lane & 3, slot = (lane & (GL - 1)) >> 2;
   const double sgx = (c == 1 || c == 2) ? 1.0 : -1.0;  // corners (-,-) (+,-) (+,+) (-,+),
@@ -256,6 +283,18 @@ __device__ __forceinline__ void dp_setup_views(const DpViewDev *__restrict__ vie
     const DpViewDev *V = views + (inr ? vid : 0);
     double u, v;
     dp_project(V->P, X0, X1, X2, u, v);
+    if (lv.tab != nullptr) {  // read this view at the level its footprint asks for
+      const double u0 = __shfl_sync(DP_FULL, u, 0, 4), v0 = __shfl_sync(DP_FULL, v, 0, 4);
+      const double u1 = __shfl_sync(DP_FULL, u, 1, 4), v1 = __shfl_sync(DP_FULL, v, 1, 4);
+      const double u3 = __shfl_sync(DP_FULL, u, 3, 4), v3 = __shfl_sync(DP_FULL, v, 3, 4);
+      const int up = dp_pick_level(xsub(u1, u0), xsub(v1, v0), xsub(u3, u0), xsub(v3, v0), lv.thr2, lv.up);
+      if (up > 0) {  // P_l = diag(2^-l, 2^-l, 1) P: the projection scales exactly
+        const double sc = __hiloint2double((1023 - up) << 20, 0);
+        u = xmul(u, sc);
+        v = xmul(v, sc);
+        V = lv.tab + ((size_t)up * n_views + (inr ? vid : 0));
+      }
+    }
     const int W = V->width, H = V->height;
     const bool in = inr && (u > 0) && (u < (double)W) && (v > 0) && (v < (double)H);
     const unsigned inm = __ballot_sync(DP_FULL, in);

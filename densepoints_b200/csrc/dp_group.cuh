@@ -467,6 +467,7 @@ __device__ __forceinline__ void dp_view_texture_rolled(const DpViewSetupG &R, in
 // the warp.  nv = 0 marks a group that does not evaluate.  Must be called by the whole warp.
 template <typename C, bool WRITE_TEX, typename Sink>
 __device__ __forceinline__ void dp_eval_views_g(const DpViewDev *__restrict__ views, int n_views,
+                                                const DpLevelSel &lv,
                                                 int ref, bool ref_ok, const int32_t *vis, int nv,
                                                 int s, int npx, const double n[3], const double p[3],
                                                 const double pc[3],
@@ -487,7 +488,7 @@ __device__ __forceinline__ void dp_eval_views_g(const DpViewDev *__restrict__ vi
     const int kc = min(max(nv - k0, 0), GROUND);   // this group's views in the round
     const int kcmax = min(GROUND, nvmax - k0);     // warp-uniform loop bound
     __syncwarp();
-    dp_setup_views<GL, DpViewSetupG>(views, n_views, vis + k0, kc, kcmax, s, f, recs, lane);
+    dp_setup_views<GL, DpViewSetupG>(views, n_views, lv, vis + k0, kc, kcmax, s, f, recs, lane);
     __syncwarp();
     unsigned my1 = 0, my2 = 0;
     double mynum = 0.0;
@@ -549,6 +550,7 @@ __device__ __forceinline__ void dp_eval_views_g(const DpViewDev *__restrict__ vi
 // over the visible views in view order (optimization_opencv.cpp:17-35).
 template <typename C>
 __device__ __forceinline__ double dp_objective_g(const DpViewDev *__restrict__ views, int n_views,
+                                                 const DpLevelSel &lv,
                                                  int ref, const int32_t *vis, int nv, int s, int npx,
                                                  const double n[3], const double p[3],
                                                  const double pc[3],
@@ -557,7 +559,7 @@ __device__ __forceinline__ double dp_objective_g(const DpViewDev *__restrict__ v
                                                  const DpGroupLane &L) {
   double sum = 0.0;
   dp_eval_views_g<C, false>(
-      views, n_views, ref, true, vis, nv, s, npx, n, p, pc, recs, txy, gs, tile, lane, L, nullptr, nullptr,
+      views, n_views, lv, ref, true, vis, nv, s, npx, n, p, pc, recs, txy, gs, tile, lane, L, nullptr, nullptr,
       [&](int k0, int kc, int kcmax, double score) {
         // std::accumulate of (1 - NCC) in view order (optimization_opencv.cpp:24, 34)
         const double term = xsub(1.0, score);
@@ -633,7 +635,7 @@ dp_score_group_kernel(DpScoreArgs a, const int32_t *__restrict__ order) {
   const double thr = a.thr;
   const unsigned lt = (1u << L.sub) - 1u;
   dp_eval_views_g<C, WRITE_TEX>(
-      a.p.views, a.p.n_views, ref, ref_ok, vis, nv, s, npx, n, p, pc,
+      a.p.views, a.p.n_views, a.p.lv, ref, ref_ok, vis, nv, s, npx, n, p, pc,
       sh.recs[warp][grp], sh.txy + L.sub, &sh.gray[warp][0][lane], sh.group_tile(warp, grp), lane, L,
       tex, valid, [&](int k0, int kc, int kcmax, double score) {
         const int k = k0 + L.sub;
@@ -746,7 +748,7 @@ __global__ void __launch_bounds__(DP_GWARPS * 32, DP_GMINCTA) dp_refine_group_ke
       dp_unparametrize_g(c3, n0, p0, S.pt[0], S.pt[1], S.pt[2], n, p, L, DP_FULL);
     }
     const int nv_eval = (have && nv >= 2 && ref_ok) ? nv : 0;
-    const double fobj = dp_objective_g<C>(a.p.views, a.p.n_views, ref_ok ? ref : 0, vis, nv_eval, s,
+    const double fobj = dp_objective_g<C>(a.p.views, a.p.n_views, a.p.lv, ref_ok ? ref : 0, vis, nv_eval, s,
                                            npx, n, p, p0, recs, txy, &sh.gray[warp][0][lane],
                                            sh.group_tile(warp, grp), lane, L);
     const double fval = nv_eval ? fobj : 2.0;  // scores.size() == 0 (optimization_opencv.cpp:30-32)

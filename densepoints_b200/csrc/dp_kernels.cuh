@@ -32,6 +32,7 @@ struct DpPatchArgs {
   float *pos, *nrm;
   int32_t *ref, *nvis, *vis;
   int s;
+  DpLevelSel lv;  // per-(patch, view) pyramid level, or tab == null
 };
 
 struct DpScoreArgs {
@@ -84,6 +85,7 @@ struct __align__(128) DpWarpShared {
 // of view 0 is meaningless).
 template <int NPASS, bool WRITE_TEX, bool STAGE, typename Sink>
 __device__ __forceinline__ void dp_eval_views(const DpViewDev *__restrict__ views, int n_views,
+                                              const DpLevelSel &lv,
                                               int ref, const int32_t *vis, int nv, int s, int npx,
                                               const double n[3], const double p[3],
                                               const double pc[3],
@@ -104,7 +106,7 @@ __device__ __forceinline__ void dp_eval_views(const DpViewDev *__restrict__ view
   for (int k0 = 0; k0 < nv; k0 += DP_ROUND) {
     const int kc = min(DP_ROUND, nv - k0);
     __syncwarp();
-    dp_setup_views<32>(views, n_views, vis + k0, kc, kc, s, f, recs, lane);
+    dp_setup_views<32>(views, n_views, lv, vis + k0, kc, kc, s, f, recs, lane);
     __syncwarp();
     unsigned my1 = 0, my2 = 0;
     double mynum = 0.0;
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(DP_WARPS * 32, dp_score_min_ctas(NPASS)) dp_sc
   const double thr = a.thr;
   const unsigned lt = (1u << lane) - 1u;
   dp_eval_views<NPASS, WRITE_TEX, true>(
-      a.p.views, a.p.n_views, ref, vis, nv, s, npx, n, p, pc, tx, ws, lane, tex, valid,
+      a.p.views, a.p.n_views, a.p.lv, ref, vis, nv, s, npx, n, p, pc, tx, ws, lane, tex, valid,
       [&](int k0, int kc, double score) {
         const int k = k0 + lane;
         const bool mine = lane < kc && k >= 1;
@@ -522,7 +524,7 @@ __global__ void __launch_bounds__(DP_RWARPS * 32, dp_refine_min_ctas(NPASS)) dp_
         double sum = 0.0;
         if (WPP == 1) {
           dp_eval_views<NPASS, false, false>(
-              a.p.views, a.p.n_views, ref, vis, nv, s, npx, n, p, p0, tx, ws, lane, nullptr,
+              a.p.views, a.p.n_views, a.p.lv, ref, vis, nv, s, npx, n, p, p0, tx, ws, lane, nullptr,
               nullptr, [&](int k0, int kc, double score) {
                 // std::accumulate of (1 - NCC) in view order (optimization_opencv.cpp:24, 34)
                 const double term = xsub(1.0, score);
@@ -531,7 +533,7 @@ __global__ void __launch_bounds__(DP_RWARPS * 32, dp_refine_min_ctas(NPASS)) dp_
               });
         } else {
           dp_eval_views<NPASS, false, false>(
-              a.p.views, a.p.n_views, ref, gvis[warp], nvw, s, npx, n, p, p0, tx, ws, lane, nullptr,
+              a.p.views, a.p.n_views, a.p.lv, ref, gvis[warp], nvw, s, npx, n, p, p0, tx, ws, lane, nullptr,
               nullptr, [&](int k0, int kc, double score) {
                 const int t = k0 + lane;  // entry of this warp's list -> view 1 + wg + (t - 1) WPP
                 if (lane < kc && t >= 1) gscore[grp][1 + wg + (t - 1) * WPP] = score;

@@ -238,13 +238,11 @@ struct DpLaneView {
 };
 
 __device__ __forceinline__ void dp_lane_setup(const DpViewDev *__restrict__ views, int n_views,
+                                              const DpLevelSel &lv,
                                               int vid, bool active, int s, double inv_s,
                                               const DpFrame &f, DpLaneView &R) {
   const bool inr = active && f.ok && vid >= 0 && vid < n_views;
   const DpViewDev *V = views + (inr ? vid : 0);
-  const int W = V->width, H = V->height;
-  int tlx = W, tly = H, brx = 0, bry = 0;  // patch.cpp:126
-  bool all_in = inr;
   double u[4], v[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
@@ -261,6 +259,25 @@ __device__ __forceinline__ void dp_lane_setup(const DpViewDev *__restrict__ view
 #else
     dp_project(V->P, X0, X1, X2, u[c], v[c]);
 #endif
+  }
+  if (lv.tab != nullptr) {  // read this view at the level its footprint asks for (dp_pick_level)
+    const int up = dp_pick_level(xsub(u[1], u[0]), xsub(v[1], v[0]), xsub(u[3], u[0]),
+                                 xsub(v[3], v[0]), lv.thr2, lv.up);
+    if (up > 0) {  // P_l = diag(2^-l, 2^-l, 1) P: the projection scales exactly
+      const double sc = __hiloint2double((1023 - up) << 20, 0);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        u[c] = xmul(u[c], sc);
+        v[c] = xmul(v[c], sc);
+      }
+      V = lv.tab + ((size_t)up * n_views + (inr ? vid : 0));
+    }
+  }
+  const int W = V->width, H = V->height;
+  int tlx = W, tly = H, brx = 0, bry = 0;  // patch.cpp:126
+  bool all_in = inr;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
     all_in = all_in && (u[c] > 0) && (u[c] < (double)W) && (v[c] > 0) && (v[c] < (double)H);
     // ROI: tl = min ceil, br = max floor over the 4 corners (patch.cpp:137-140)
     tlx = min(tlx, __double2int_ru(u[c]));
@@ -482,7 +499,7 @@ dp_score_lane_kernel(DpScoreArgs a, const int32_t *__restrict__ order) {
     const bool active = k < nv;
     const int vid = active ? vis[k] : -1;
     DpLaneView R;
-    dp_lane_setup(a.p.views, a.p.n_views, vid, active, S, inv_s, f, R);
+    dp_lane_setup(a.p.views, a.p.n_views, a.p.lv, vid, active, S, inv_s, f, R);
     int tpitch, xoff;
     const bool staged = dp_lane_stage(R, R.ok && R.tame, warp_tiles + lane * DP_LTSTR, tpitch, xoff);
     dp_cp_async_wait_all();
@@ -620,7 +637,7 @@ __global__ void __launch_bounds__(DP_LWARPS * 32, DP_LMINCTA) dp_refine_lane_ker
     for (int k = 0; k < nvmax; ++k) {
       const bool active = k < nv_eval;
       DpLaneView R;
-      dp_lane_setup(a.p.views, a.p.n_views, active ? vis[k] : -1, active, S, inv_s, f, R);
+      dp_lane_setup(a.p.views, a.p.n_views, a.p.lv, active ? vis[k] : -1, active, S, inv_s, f, R);
       int tpitch, xoff;
       const bool staged = dp_lane_stage(R, R.ok && R.tame, warp_tiles + lane * DP_LTSTR, tpitch, xoff);
       dp_cp_async_wait_all();

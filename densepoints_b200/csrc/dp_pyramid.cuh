@@ -77,6 +77,22 @@ extern "C" int dp_build_pyramid(dp_context *ctx, int n_levels) {
     ctx->views_dirty = true;
     ctx->org.ready = false;
   }
+  if (ctx->auto_level) ctx->views_dirty = true;  // the table of the levels above the base changed
+  return DP_OK;
+}
+
+// Per-(patch, view) level selection.  Off: every view is read at the level
+// dp_set_level chose.  On: that level is the BASE -- patch frame, visibility, proposals, grids and
+// colours stay on it -- and GetProjectedTextures reads view v of a patch at base + k(p, v), k =
+// the number of halvings that bring the patch's projected quad in v below px_per_cell pixels per
+// texel (dp_pick_level), capped at the coarsest level built.
+extern "C" int dp_set_level_selection(dp_context *ctx, int enable, double px_per_cell) {
+  if (!ctx) return DP_ERR_INVALID_ARG;
+  if (enable && !(px_per_cell > 0.0 && px_per_cell < 1e6))
+    return dp_fail(ctx, DP_ERR_INVALID_ARG, "px_per_cell");
+  ctx->auto_level = enable != 0;
+  if (enable) ctx->level_px = px_per_cell;
+  ctx->views_dirty = true;
   return DP_OK;
 }
 

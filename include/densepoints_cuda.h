@@ -247,6 +247,17 @@ int dp_export_ply(dp_context *ctx, const char *path);
  * device for every uploaded view; dp_set_level selects the level all later calls use. */
 int dp_build_pyramid(dp_context *ctx, int n_levels);
 int dp_set_level(dp_context *ctx, int level);
+/* Per-(patch, view) level selection (north_star item 2, "at the chosen pyramid level"; no
+ * reference semantics: options.h:10 `scale` is dead, modules/image/Image.h:1-7 a placeholder).
+ * enable = 0: every view is read at the level dp_set_level chose (default).  enable = 1: that
+ * level is the base (patch frame, visibility, proposals, grids, colours); the texture of view v
+ * of a patch is taken from level base + k, k = the number of halvings that bring the longer of
+ * the two sides of the patch's projected quad through corner 0 below px_per_cell * cell_size
+ * base-level pixels (a texel then covers < px_per_cell pixels of the level it is sampled
+ * from), capped at the coarsest level built.  The result is by definition the reference path
+ * (GetProjectedTextures, optimization.cpp:14-56) run on pyrDown^k of view v with
+ * P_k = diag(2^-k, 2^-k, 1) P; scoring, filter, refinement and expansion all use it. */
+int dp_set_level_selection(dp_context *ctx, int enable, double px_per_cell);
 int dp_download_level(dp_context *ctx, int view_id, int level, uint8_t *bgr, size_t capacity,
                       int *width, int *height);
 

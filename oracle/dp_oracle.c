@@ -622,6 +622,46 @@ int orc_patch_homography(const orc_view *v, int cell_size, const double pos[3], 
   return 1;
 }
 
+/* ---- per-(patch, view) pyramid level ------------------------------------------
+ * The reference has no semantics for this (modules/image/Image.h:1-7 is a placeholder,
+ * options.h:10 `scale` is dead); the definition is: view v of a patch is read from
+ * pyrDown^k(image_v) with P_k = diag(2^-k, 2^-k, 1) P, i.e. the reference path
+ * (optimization.cpp:14-56) on the level views, k = the number of halvings that bring the longer
+ * of the two quad sides through corner 0 (patch.cpp:119-123 corners, projected with the base
+ * view) below px_per_cell * cell_size pixels.  Level tables are registered once
+ * (orc_set_level_selection); level 0 of the table must be the `views` array the calls get. */
+static const orc_view *g_lv_views = NULL;
+static int g_lv_levels = 0, g_lv_nviews = 0;
+static double g_lv_px = 1.5;
+void orc_set_level_selection(const orc_view *levels, int n_levels, int n_views, double px_per_cell) {
+  g_lv_views = (levels && n_levels > 1) ? levels : NULL;
+  g_lv_levels = n_levels;
+  g_lv_nviews = n_views;
+  g_lv_px = px_per_cell;
+}
+int orc_pick_level(const orc_view *v, int cell_size, const double pos[3], const double ax[3],
+                   const double ay[3], double px_per_cell, int max_up) {
+  static const double sgn[3][2] = {{-1, -1}, {+1, -1}, {-1, +1}}; /* corners 0, 1, 3 */
+  double uv[3][2];
+  for (int i = 0; i < 3; ++i) {
+    double X[3];
+    for (int j = 0; j < 3; ++j) X[j] = pos[j] + sgn[i][0] * ax[j] + sgn[i][1] * ay[j];
+    orc_project(v, X, uv[i]);
+  }
+  double du1 = uv[1][0] - uv[0][0], dv1 = uv[1][1] - uv[0][1];
+  double du3 = uv[2][0] - uv[0][0], dv3 = uv[2][1] - uv[0][1];
+  double a = du1 * du1 + dv1 * dv1, b = du3 * du3 + dv3 * dv3;
+  double d2 = (b > a) ? b : a;
+  double side = px_per_cell * (double)cell_size;
+  double t = side * side;
+  int k = 0;
+  while (k < max_up && d2 >= t) {
+    ++k;
+    t = t * 4.0;
+  }
+  return k;
+}
+
 /* Optimization::GetProjectedTextures(normal, position, textures) (optimization.cpp:14-56).
  * `nrm` / `pos` are the ARGUMENTS: they only feed GetProjectedXYAxisAndScale (:24-26), i.e.
  * the patch axes and dx.  The four corners are built around `centre` = patch_.GetPosition(),
@@ -645,6 +685,10 @@ void orc_projected_textures(const orc_view *views, int ref, const int *vis, int 
   }
   for (int k = 0; k < nvis; ++k) {
     const orc_view *v = &views[vis[k]];
+    if (g_lv_views) { /* the level this view is read at */
+      int up = orc_pick_level(v, cell_size, centre, ax, ay, g_lv_px, g_lv_levels - 1);
+      v = &g_lv_views[(size_t)up * g_lv_nviews + vis[k]];
+    }
     double H[9], M[9];
     int roi[4];
     int ok;
@@ -666,6 +710,29 @@ void orc_projected_textures(const orc_view *views, int ref, const int *vis, int 
     else
       warp_with_M(src, v->stride, roi[2], roi[3], M, s, dst);
     valid[k] = 1;
+  }
+}
+
+/* the level every (patch, visible view) pair is read at under the registered selection
+ * (test statistics: out[i * vstride + k], -1 where there is no view or no selection) */
+void orc_levels_batch(const orc_view *views, const float *pos, const float *nrm, const int *ref,
+                      const int *nvis, const int *vis, int vstride, int n, int cell_size, int *out) {
+  for (int i = 0; i < n; ++i) {
+    double nn[3] = {nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]};
+    double pp[3] = {pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]};
+    double xa[3], ya[3], dx;
+    for (int k = 0; k < vstride; ++k) out[(size_t)i * vstride + k] = -1;
+    if (!g_lv_views) continue;
+    orc_axes_scale(&views[ref[i]], nn, pp, xa, ya, &dx);
+    if (dx == 0 || !isfinite(dx)) continue;
+    double scale = (double)(cell_size / 2) / dx, ax[3], ay[3];
+    for (int j = 0; j < 3; ++j) {
+      ax[j] = scale * xa[j];
+      ay[j] = scale * ya[j];
+    }
+    for (int k = 0; k < nvis[i] && k < vstride; ++k)
+      out[(size_t)i * vstride + k] = orc_pick_level(&views[vis[(size_t)i * vstride + k]], cell_size,
+                                                    pp, ax, ay, g_lv_px, g_lv_levels - 1);
   }
 }
 

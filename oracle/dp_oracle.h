@@ -61,6 +61,15 @@ typedef struct orc_params {
 
 void orc_default_params(orc_params *p);
 
+/* Per-(patch, view) pyramid level (see dp_oracle.c): levels = [n_levels][n_views] view tables,
+ * level 0 first (must be the array later calls pass as `views`); NULL or n_levels <= 1 = off. */
+void orc_set_level_selection(const orc_view *levels, int n_levels, int n_views, double px_per_cell);
+void orc_levels_batch(const orc_view *views, const float *pos, const float *nrm, const int *ref,
+                      const int *nvis, const int *vis, int vstride, int n, int cell_size, int *out);
+int orc_pick_level(const orc_view *v, int cell_size, const double pos[3], const double ax[3],
+                   const double ay[3], double px_per_cell, int max_up);
+
+
 /* ---- modules/core ---------------------------------------------------- */
 /* View::SetProjectionMatrix (types.cpp:28-68): K, R (3x3 row-major), centre. */
 void orc_view_decompose(const double P[12], double K[9], double R[9], double center[3]);

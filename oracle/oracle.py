@@ -367,6 +367,40 @@ class Organizer:
         return lib().orc_expand_patches_fifo(self.h, C.c_int(cell_size), C.c_longlong(max_pops))
 
 
+_level_tables = None      # keeps the registered level table (and its Views) alive
+
+
+def set_level_selection(levels, px_per_cell=1.5):
+    """Per-(patch, view) pyramid level (dp_oracle.c): levels = [Views of level 0 (the base: the
+    object later calls pass as `views`), Views of level 1, ...] or None to switch it off."""
+    global _level_tables
+    if not levels or len(levels) < 2:
+        lib().orc_set_level_selection(None, C.c_int(0), C.c_int(0), C.c_double(px_per_cell))
+        _level_tables = None
+        return
+    nv = levels[0].n
+    tab = (OrcView * (nv * len(levels)))()
+    tab_p = C.cast(tab, C.POINTER(OrcView))
+    for l, V in enumerate(levels):
+        assert V.n == nv
+        for i in range(nv):
+            C.memmove(C.byref(tab, (l * nv + i) * C.sizeof(OrcView)), C.byref(V.arr[i]), C.sizeof(OrcView))
+    # level 0 of the table must BE the base array (the C side indexes the table by view id and
+    # takes the frame from the `views` argument): same contents, so either works
+    lib().orc_set_level_selection(tab_p, C.c_int(len(levels)), C.c_int(nv), C.c_double(px_per_cell))
+    _level_tables = (tab, list(levels))
+
+
+def levels_batch(views, pos, nrm, ref, nvis, vis, cell_size):
+    """The level each (patch, visible view) pair is read at under the registered selection."""
+    pos, nrm, ref, nvis, vis = _f32(pos), _f32(nrm), _i32(ref), _i32(nvis), _i32(vis)
+    n, vs = vis.shape
+    out = np.full((n, vs), -1, np.int32)
+    lib().orc_levels_batch(views.arr, _p(pos), _p(nrm), _p(ref), _p(nvis), _p(vis), C.c_int(vs),
+                           C.c_int(n), C.c_int(cell_size), _p(out))
+    return out
+
+
 def set_homography_mode(mode: int):
     """0 = OpenCV's DLT + eigen-solve + inversion (pinned against cv2); 1 = exact closed form
     (deterministic at ties; what the CUDA path is checked against).  See dp_oracle.h."""

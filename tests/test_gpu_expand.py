@@ -151,6 +151,114 @@ def test_scoring_on_pyramid_level(capi_mod, exact_orc):
     ctx.close()
 
 
+def _zoomed_scene(zoom, n_seeds, width=480, height=360, seed=7):
+    """A plane scene whose view i is delivered at `zoom[i]` times the resolution (pixel
+    replication, P_i' = diag(z, z, 1) P_i): the same patch then covers 1, 2, 3 or 4 pixels per
+    texel depending on the view, which is what per-(patch, view) level selection is for."""
+    from densepoints_b200 import scenes
+    sc = scenes.make_plane_scene(seed=seed, n_views=len(zoom), width=width, height=height,
+                                 yaw_spread_deg=16.0)
+    seeds = scenes.make_seeds(sc, n_seeds, seed=seed + 2, depth_noise=0.004, tilt_deg=5.0)
+    Ps, imgs = [], []
+    for P, im, z in zip(sc.P, sc.images, zoom):
+        Pz = P.copy()
+        Pz[:2, :] *= float(z)
+        Ps.append(Pz)
+        imgs.append(np.ascontiguousarray(np.repeat(np.repeat(im, z, axis=0), z, axis=1)))
+    return np.array(Ps), imgs, seeds
+
+
+def _level_views(orc, Ps, imgs, n_levels):
+    out = [orc.Views(Ps, imgs)]
+    for _ in range(1, n_levels):
+        imgs = [orc.pyrdown(im) for im in imgs]            # pinned against cv2.pyrDown
+        Ps = Ps.copy()
+        Ps[:, :2, :] *= 0.5
+        out.append(orc.Views(Ps, imgs))
+    return out
+
+
+@pytest.mark.parametrize("s,env", [(7, {"DP_LANE_MIN_PATCHES": "0"}), (7, {"DP_REFINE_KERNEL": "group", "DP_SCORE_KERNEL": "group"}),
+                                   (5, {"DP_LANE_MIN_PATCHES": "0"}), (11, {}), (20, {})])
+def test_per_view_level_selection(capi_mod, exact_orc, monkeypatch, s, env):
+    """dp_set_level_selection: the texture of view v of a patch comes from the pyramid level its
+    projected footprint asks for -- by definition the reference path (optimization.cpp:14-56) on
+    pyrDown^k of that view with P_k = diag(2^-k, 2^-k, 1) P.  Textures, scores, the filter and
+    the refinement (every kernel family: one patch per lane, four lanes per patch, one warp per
+    patch) against the oracle, on a scene whose views deliver 1x, 2x, 3x and 4x the reference
+    resolution so that levels 0, 1 and 2 all occur."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    zoom = [1, 2, 1, 4, 3, 2]
+    Ps, imgs, seeds = _zoomed_scene(zoom, 900)
+    ctx = capi_mod.Context(0, capi_mod.default_params(minimum_visible_image=2))
+    ctx.set_views(Ps, imgs)
+    ctx.build_pyramid(3)
+    ctx.set_level_selection(True, 1.25)
+    lv = _level_views(exact_orc, Ps, imgs, 3)
+    V = lv[0]
+    pos, nrm, ref = seeds["pos"], seeds["nrm"], seeds["ref"]
+    nvis, vis, _, _ = ctx.visibility(pos, nrm, ref)           # on the base level
+    o = exact_orc.visibility_batch(V, pos, nrm, ref)
+    assert np.array_equal(nvis, o[0]) and np.array_equal(vis, o[1])
+    exact_orc.set_level_selection(lv, 1.25)
+    try:
+        picked = exact_orc.levels_batch(V, pos, nrm, ref, nvis, vis, s)
+        counts = [int((picked == l).sum()) for l in range(3)]
+        assert min(counts) > 50, counts                       # the three levels really mix
+        ncc, tex, valid = ctx.score(pos, nrm, ref, nvis, vis, s, want_tex=True)
+        o_ncc, o_tex, o_valid = exact_orc.score_batch(V, pos, nrm, ref, nvis, vis, s, want_tex=True)
+        assert np.array_equal(valid, o_valid) and np.array_equal(tex, o_tex)
+        assert np.abs(ncc - o_ncc).max() < 1e-6
+        assert valid.sum() > 0.5 * (nvis.sum())
+        keep, fnv, fvi = ctx.filter(pos, nrm, ref, nvis, vis, s)
+        o_keep, o_fnv, o_fvi = exact_orc.filter_batch(V, pos, nrm, ref, nvis, vis, s, min_visible=2)
+        assert np.array_equal(keep, o_keep) and np.array_equal(fnv, o_fnv) and np.array_equal(fvi, o_fvi)
+        m = np.where(keep.astype(bool))[0][:250]
+        p1, n1, ev, _ = ctx.refine(pos[m], nrm[m], ref[m], fnv[m], fvi[m], s)
+        o_p, o_n, o_ev, _ = exact_orc.refine_batch(V, pos[m], nrm[m], ref[m], fnv[m], fvi[m], s,
+                                                   exact_orc.default_params(minimum_visible_image=2))
+        assert np.array_equal(ev, o_ev) and np.array_equal(p1, o_p) and np.array_equal(n1, o_n)
+        # switched off again: back to the base level for every view
+        ctx.set_level_selection(False)
+        exact_orc.set_level_selection(None)
+        ncc0 = ctx.score(pos, nrm, ref, nvis, vis, s)
+        assert np.abs(ncc0 - exact_orc.score_batch(V, pos, nrm, ref, nvis, vis, s)).max() < 1e-6
+        assert np.abs(ncc0 - ncc).max() > 1e-3                # and it does make a difference
+    finally:
+        exact_orc.set_level_selection(None)
+        ctx.close()
+
+
+def test_expansion_with_level_selection(capi_mod, exact_orc):
+    """The expansion loop (refine + filter of every candidate) under per-view level selection:
+    store and grids against the 1-thread FIFO oracle."""
+    zoom = [1, 2, 1, 3]
+    Ps, imgs, seeds = _zoomed_scene(zoom, 120, width=320, height=240, seed=11)
+    ctx = capi_mod.Context(0, capi_mod.default_params(minimum_visible_image=2))
+    ctx.set_views(Ps, imgs)
+    ctx.build_pyramid(3)
+    ctx.set_level_selection(True, 1.5)
+    lv = _level_views(exact_orc, Ps, imgs, 3)
+    V = lv[0]
+    prm = exact_orc.default_params(minimum_visible_image=2)
+    nvis, vis, _, _ = exact_orc.visibility_batch(V, seeds["pos"], seeds["nrm"], seeds["ref"])
+    exact_orc.set_level_selection(lv, 1.5)
+    try:
+        org = exact_orc.Organizer(V, prm)
+        acc_o = org.set_seeds(seeds["pos"], seeds["nrm"], seeds["ref"], nvis, vis)
+        ctx.organizer_reset()
+        acc = ctx.organizer_insert(seeds["pos"], seeds["nrm"], seeds["ref"], nvis, vis)
+        assert np.array_equal(acc, acc_o)
+        stats = ctx.expand(5, 2)
+        assert stats["pops"] == org.expand(5, 2)
+        assert ctx.organizer_size() > int(acc.sum())          # something was expanded
+        _same_store(ctx, org, len(zoom))
+    finally:
+        exact_orc.set_level_selection(None)
+        ctx.close()
+
+
 def test_create_patches_and_ply_export(capi_mod, exact_orc, tmp_path):
     """SURVEY 8f: Seed::CreatePatchesFromPoints on the device; PLY export of the store."""
     from densepoints_b200 import scenes

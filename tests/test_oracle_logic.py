@@ -185,3 +185,61 @@ def test_downhill_upstream_regression_cases(orc):
     rosen = lambda x: float(100 * (x[1] - x[0] ** 2) ** 2 + (1 - x[0]) ** 2)
     x, res, fc = orc.downhill(rosen, [0.0, 0.0], [0.5, 0.5], max_evals=5000, eps=1e-6)
     assert abs(res) < 1e-2 and np.abs(x - 1.0).max() < 1e-2
+
+
+def test_level_selection_follows_its_definition(orc):
+    """Per-(patch, view) pyramid level (dp_set_level_selection): by definition the
+    texture of view v read at level k is what the reference path gives on cv2.pyrDown^k of that
+    view with P_k = diag(2^-k, 2^-k, 1) P while the patch frame still comes from the base-level
+    reference view.  Checked by running the oracle WITHOUT selection on view sets in which every
+    view but the reference one is replaced by its level-k version (images from the real
+    cv2.pyrDown) and picking, pair by pair, the level the selection rule reports."""
+    cv2 = pytest.importorskip("cv2")
+    from densepoints_b200 import scenes
+    zoom = [1, 2, 4]
+    sc = scenes.make_plane_scene(seed=7, n_views=3, width=240, height=180, yaw_spread_deg=14.0)
+    seeds = scenes.make_seeds(sc, 150, seed=9, depth_noise=0.004, tilt_deg=5.0)
+    P0, I0 = [], []
+    for P, im, z in zip(sc.P, sc.images, zoom):
+        Pz = P.copy()
+        Pz[:2, :] *= float(z)
+        P0.append(Pz)
+        I0.append(np.ascontiguousarray(np.repeat(np.repeat(im, z, axis=0), z, axis=1)))
+    Ps, Is = [np.array(P0)], [I0]
+    for _ in (1, 2):
+        Ps.append(Ps[-1].copy())
+        Ps[-1][:, :2, :] *= 0.5
+        Is.append([cv2.pyrDown(im) for im in Is[-1]])
+    lv = [orc.Views(P, I) for P, I in zip(Ps, Is)]
+    pos, nrm, ref = seeds["pos"], seeds["nrm"], seeds["ref"]
+    nvis, vis, _, _ = orc.visibility_batch(lv[0], pos, nrm, ref)
+    s = 7
+    orc.set_level_selection(lv, 1.5)
+    try:
+        picked = orc.levels_batch(lv[0], pos, nrm, ref, nvis, vis, s)
+        ncc, tex, valid = orc.score_batch(lv[0], pos, nrm, ref, nvis, vis, s, want_tex=True)
+    finally:
+        orc.set_level_selection(None)
+    assert all((picked == l).sum() > 20 for l in range(3))
+    checked = 0
+    for r in range(3):
+        sel = np.where(ref == r)[0]
+        if len(sel) == 0:
+            continue
+        for l in range(3):
+            W = orc.Views([Ps[l][v] if v != r else Ps[0][r] for v in range(3)],
+                          [Is[l][v] if v != r else Is[0][r] for v in range(3)])
+            _, t_l, v_l = orc.score_batch(W, pos[sel], nrm[sel], ref[sel], nvis[sel], vis[sel], s,
+                                          want_tex=True)
+            for a, i in enumerate(sel):
+                for k in range(nvis[i]):
+                    if picked[i, k] == l and vis[i, k] != r:
+                        assert valid[i, k] == v_l[a, k]
+                        assert np.array_equal(tex[i, k], t_l[a, k])
+                        checked += 1
+    assert checked > 100
+    # the reference view of a patch is sampled at ~1 pixel per texel by construction of the
+    # patch frame (optimization.cpp:19-30), i.e. always at the base level
+    k0 = np.arange(vis.shape[1])[None, :]
+    is_ref = (vis == ref[:, None]) & (k0 < nvis[:, None])
+    assert (picked[is_ref] == 0).all()
