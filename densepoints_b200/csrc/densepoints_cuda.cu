@@ -67,8 +67,8 @@ extern "C" int dp_abi_version(void) { return DP_ABI_VERSION; }
 
 static int check_params(dp_context *ctx, const dp_params *p) {
   if (p->grid_scale <= 0) return dp_fail(ctx, DP_ERR_INVALID_ARG, "grid_scale must be > 0");
-  if (p->max_patches_per_cell != 1)
-    return dp_fail(ctx, DP_ERR_INVALID_ARG, "only max_patches_per_cell == 1 is supported");
+  if (p->max_patches_per_cell < 1 || p->max_patches_per_cell > 255)
+    return dp_fail(ctx, DP_ERR_INVALID_ARG, "max_patches_per_cell must be in [1, 255]");
   if (p->nm_max_evals < 4) return dp_fail(ctx, DP_ERR_INVALID_ARG, "nm_max_evals must be >= 4");
   return DP_OK;
 }
@@ -126,7 +126,7 @@ extern "C" void dp_destroy(dp_context *ctx) {
                       &ctx->s_keep, &ctx->s_evals, &ctx->s_xbest, &ctx->s_cand, &ctx->s_ncand,
                       &ctx->s_img, &ctx->s_misc, &ctx->work_counter, &ctx->s_order, &ctx->d_views_lv, &ctx->s_nmsave, &ctx->s_pending, &ctx->e_pos, &ctx->e_nrm,
                       &ctx->e_ref, &ctx->e_nvis, &ctx->e_vis, &ctx->e_keep, &ctx->e_seq,
-                      &ctx->e_cells, &ctx->e_recs, &ctx->e_flags, &ctx->e_scan, &ctx->e_count, &ctx->org.grid,
+                      &ctx->e_cells, &ctx->e_recs, &ctx->e_flags, &ctx->e_scan, &ctx->e_count, &ctx->e_won, &ctx->org.grid,
                       &ctx->org.claim, &ctx->org.pos, &ctx->org.nrm, &ctx->org.rgb, &ctx->org.ref,
                       &ctx->org.nvis, &ctx->org.vis};
   for (DpDevBuf *b : bufs) b->release();

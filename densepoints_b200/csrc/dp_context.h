@@ -103,7 +103,7 @@ struct dp_context {
   cudaStream_t scratch_stream = nullptr;
   bool scratch_busy = false;
   // expansion scratch
-  DpDevBuf e_pos, e_nrm, e_ref, e_nvis, e_vis, e_keep, e_seq, e_cells, e_recs, e_flags, e_scan, e_count;
+  DpDevBuf e_pos, e_nrm, e_ref, e_nvis, e_vis, e_keep, e_seq, e_cells, e_recs, e_flags, e_scan, e_count, e_won;
   DpOrganizer org;
   long long org_last_candidates = 0;
   int sm_count = 148;

@@ -92,6 +92,59 @@ dp_cells_kernel(const DpViewDev *__restrict__ views, int n_views, const uint32_t
   }
 }
 
+// max_patches_per_cell = m > 1 (patch_organizer.cpp:21): a cell takes the first m patches that
+// ask for it, in sequence order, over all levels.  The same claim / take pair runs m times: in
+// round j the lowest sequence id still asking for a cell that is not full takes a slot of it and
+// stops asking (its bit in `won`, a view mask per record); after m rounds nobody can win any more.
+// That is exactly the sequential outcome: the requesters of a cell are served in ascending
+// sequence id until it holds m patches.
+//   MODE 0 (claim)  (record, visible view) pairs that have not won ask with atomicMin(seq)
+//   MODE 1 (count)  accepted iff the record won > 1 cells (patch_organizer.cpp:58)
+//   MODE 2 (take)   the winner of a cell occupies one more slot; the claim is reset
+template <int MODE>
+__global__ void __launch_bounds__(256)
+dp_cells_multi_kernel(const DpViewDev *__restrict__ views, int n_views,
+                      const uint32_t *__restrict__ rec, long long n_rec, double grid_scale, int m,
+                      uint8_t *__restrict__ grid, unsigned int *__restrict__ claim,
+                      unsigned int *__restrict__ won, unsigned int *__restrict__ flags,
+                      uint8_t *__restrict__ accepted) {
+  const int lane = threadIdx.x & 31;
+  const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n_rec) return;
+  const int mw = dp_mask_words(n_views);
+  const uint32_t *R = rec + (size_t)r * rec_words(n_views);
+  unsigned int *Wn = won + (size_t)r * mw;
+  const uint32_t seq = R[0];
+  if (MODE == 1) {
+    unsigned wins = 0;
+    for (int w = lane; w < mw; w += 32) wins += __popc(Wn[w]);
+    wins = __reduce_add_sync(DP_FULL, wins);
+    if (lane == 0) {
+      const bool acc = wins > 1;
+      if (acc) flags[seq] = 1u;
+      if (accepted) accepted[r] = acc ? 1 : 0;
+    }
+    return;
+  }
+  const double p0 = (double)__uint_as_float(R[2]), p1 = (double)__uint_as_float(R[3]),
+               p2 = (double)__uint_as_float(R[4]);
+  for (int v = lane; v < n_views; v += 32) {
+    if (!((R[DP_REC_HDR + (v >> 5)] >> lane) & 1u)) continue;
+    if ((Wn[v >> 5] >> lane) & 1u) continue;  // has its slot already
+    const long long cell = dp_cell_of(views + v, p0, p1, p2, grid_scale);
+    if (cell < 0) continue;
+    if (MODE == 0) {
+      if ((int)grid[cell] < m) atomicMin(claim + cell, seq);
+    } else {
+      if (claim[cell] == seq) {  // one winner per cell and round
+        grid[cell] = (uint8_t)(grid[cell] + 1);
+        claim[cell] = 0xffffffffu;
+        atomicOr(Wn + (v >> 5), 1u << lane);
+      }
+    }
+  }
+}
+
 // K6d: append accepted records to the store at n0 + rank(seq).
 __global__ void __launch_bounds__(256)
 dp_append_kernel(const uint32_t *__restrict__ rec, long long n_rec, int n_views,
@@ -461,11 +514,28 @@ static int org_commit(dp_context *ctx, const uint32_t *rec, long long n_rec, lon
   const unsigned gw = (unsigned)((tw + 255) / 256);
   uint8_t *grid = o.grid.as<uint8_t>();
   unsigned int *claim = o.claim.as<unsigned int>();
-  dp_cells_kernel<0><<<gw, 256, 0, st>>>(views, nviews, rec, n_rec, gs, grid, claim, flags, nullptr);
-  dp_cells_kernel<1><<<gw, 256, 0, st>>>(views, nviews, rec, n_rec, gs, grid, claim, flags,
-                                         accepted_dev);
-  dp_cells_kernel<2><<<gw, 256, 0, st>>>(views, nviews, rec, n_rec, gs, grid, claim, flags, nullptr);
-  ctx->launches += 3;
+  const int m = ctx->prm.max_patches_per_cell;
+  if (m == 1) {
+    dp_cells_kernel<0><<<gw, 256, 0, st>>>(views, nviews, rec, n_rec, gs, grid, claim, flags, nullptr);
+    dp_cells_kernel<1><<<gw, 256, 0, st>>>(views, nviews, rec, n_rec, gs, grid, claim, flags,
+                                           accepted_dev);
+    dp_cells_kernel<2><<<gw, 256, 0, st>>>(views, nviews, rec, n_rec, gs, grid, claim, flags, nullptr);
+    ctx->launches += 3;
+  } else {
+    const size_t won_bytes = (size_t)n_rec * dp_mask_words(nviews) * 4;
+    DP_CUDA(ctx, ctx->e_won.ensure(won_bytes));
+    unsigned int *won = ctx->e_won.as<unsigned int>();
+    DP_CUDA(ctx, cudaMemsetAsync(won, 0, won_bytes, st));
+    for (int round = 0; round < m; ++round) {
+      dp_cells_multi_kernel<0><<<gw, 256, 0, st>>>(views, nviews, rec, n_rec, gs, m, grid, claim, won,
+                                                   flags, nullptr);
+      dp_cells_multi_kernel<2><<<gw, 256, 0, st>>>(views, nviews, rec, n_rec, gs, m, grid, claim, won,
+                                                   flags, nullptr);
+    }
+    dp_cells_multi_kernel<1><<<gw, 256, 0, st>>>(views, nviews, rec, n_rec, gs, m, grid, claim, won,
+                                                 flags, accepted_dev);
+    ctx->launches += 2 * m + 1;
+  }
   DP_CUDA(ctx, cudaGetLastError());
   int rc = dp_exclusive_scan(ctx, flags, offs, seq_space, st);
   if (rc != DP_OK) return rc;

@@ -48,7 +48,7 @@ typedef struct dp_params {
   double visible_threshold;   /* Patch::InitRelatedImages, patch.h:56      (0.78) */
   double candidate_threshold; /* Patch::InitRelatedImages, patch.h:57      (1.04) */
   int32_t grid_scale;         /* PatchOrganizerOptions, patch_organizer.h:43 (8)  */
-  int32_t max_patches_per_cell; /* PatchOrganizerOptions, patch_organizer.h:42 (1; only 1 supported) */
+  int32_t max_patches_per_cell; /* PatchOrganizerOptions, patch_organizer.h:42 (1); 1..255 */
   double nm_step[3];          /* OptimizationOpenCV::Optimize, optimization_opencv.cpp:56 (0.02,0.2,0.2) */
   int32_t nm_max_evals;       /* TermCriteria maxCount, optimization_opencv.cpp:60 (500) */
   double nm_eps;              /* TermCriteria epsilon,  optimization_opencv.cpp:60 (1e-4) */

@@ -80,6 +80,35 @@ def test_expansion_matches_fifo_oracle(capi_mod, exact_orc, levels):
     ctx.close()
 
 
+@pytest.mark.parametrize("m", [2, 3])
+def test_several_patches_per_cell(capi_mod, exact_orc, m):
+    """PatchOrganizerOptions::max_patches_per_cell > 1 (patch_organizer.h:40-47,
+    patch_organizer.cpp:21): a cell takes the first m patches that ask for it in insertion
+    order.  Seeds dense enough that cells fill up (grid_scale 8 on 160x120 = 300 cells per view),
+    then two expansion levels: accept bits, grids (counts up to m) and store against the oracle."""
+    from densepoints_b200 import scenes
+    sc = scenes.make_plane_scene(seed=5, n_views=4, width=160, height=120, yaw_spread_deg=14.0)
+    seeds = scenes.make_seeds(sc, 900, seed=6, depth_noise=0.004, tilt_deg=4.0)
+    ctx = capi_mod.Context(0, capi_mod.default_params(minimum_visible_image=2, max_patches_per_cell=m))
+    ctx.set_views(sc.P, sc.images)
+    V = exact_orc.Views(sc.P, sc.images)
+    prm = exact_orc.default_params(minimum_visible_image=2, max_patches_per_cell=m)
+    nvis, vis, _, _ = exact_orc.visibility_batch(V, seeds["pos"], seeds["nrm"], seeds["ref"])
+    org = exact_orc.Organizer(V, prm)
+    acc_o = org.set_seeds(seeds["pos"], seeds["nrm"], seeds["ref"], nvis, vis)
+    ctx.organizer_reset()
+    acc = ctx.organizer_insert(seeds["pos"], seeds["nrm"], seeds["ref"], nvis, vis)
+    assert np.array_equal(acc, acc_o)
+    grids = [ctx.organizer_grid(v) for v in range(sc.n_views)]
+    assert max(int(g.max()) for g in grids) == m              # some cell did fill up
+    assert 0 < acc.sum() < len(acc)                           # and some seeds were turned away
+    _same_store(ctx, org, sc.n_views)
+    stats = ctx.expand(5, 2)
+    assert stats["pops"] == org.expand(5, 2)
+    _same_store(ctx, org, sc.n_views)
+    ctx.close()
+
+
 def test_expansion_default_params_cell11(capi_mod, exact_orc):
     """Reference defaults: cell_size 11 (expand.h:12), minimum_visible_image 3."""
     sc, seeds, ctx, V, prm, nvis, vis = _setup(capi_mod, exact_orc, 6, 240, 180, 60, 3, seed=9)

@@ -423,9 +423,9 @@ def test_params_and_error_paths(capi_mod, c1):
     ctx = c1["ctx"]
     p = ctx.get_params()
     assert p.minimum_visible_image == 2 and p.score_threshold == 0.6
-    bad = capi_mod.default_params(max_patches_per_cell=2)
+    bad = capi_mod.default_params(max_patches_per_cell=0)
     with pytest.raises(capi_mod.DpError):
-        ctx.set_params(bad)                                  # only 1 patch per cell is supported
+        ctx.set_params(bad)                                  # 1..255 patches per cell
     with pytest.raises(capi_mod.DpError):
         capi_mod.Context(0, capi_mod.default_params(grid_scale=0))
     fresh = capi_mod.Context(0)
