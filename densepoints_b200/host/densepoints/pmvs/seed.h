@@ -80,10 +80,7 @@ class SeedCUDA {
                     "dp_filter_refine");
     b.StoreVisible(ptr.data());
     b.StoreGeometry(ptr.data());
-    std::vector<size_t> to_remove;
-    for (size_t i = 0; i < keep.size(); ++i)
-      if (!keep[i]) to_remove.push_back(i);
-    RemovePatches(to_remove);
+    KeepPatches(patches_, keep);  // = RemovePatches of the patches the filter dropped
   }
   void FilterPatches() {  // seed.cpp:110-126
     if (patches_.empty()) return;

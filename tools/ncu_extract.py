@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--source", default="")
     ap.add_argument("--hbm-evals-score", type=int, default=0)
     ap.add_argument("--hbm-evals-refine", type=int, default=0)
+    ap.add_argument("--hbm-refine-raw", default="", help="raw csv of a light metrics pass over the refine launch")
     ap.add_argument("--src-sha256", default="", help="hash printed by the profiled run (default: this tree)")
     a = ap.parse_args()
     sha = a.src_sha256 or source_hash()
@@ -82,7 +83,16 @@ def main():
              "score_duration_ms_under_ncu": dur_s,
              "score_warp_inst_per_launch": gs("smsp__inst_executed.sum")}
         if a.hbm_evals_refine:
-            dr, gr, dram_r, dur_r = pick("refine")
+            if a.hbm_refine_raw:  # the 0.6 s refine launch: DRAM bytes and duration only (one pass)
+                rows2 = list(csv.reader(open(a.hbm_refine_raw)))
+                h2, u2 = rows2[0], rows2[1]
+                r2 = [r for r in rows2[2:] if "refine" in r[h2.index("Kernel Name")]][-1]
+                g2 = lambda k: float(r2[h2.index(k)])
+                dram_r = sum(g2(k) * to_bytes[u2[h2.index(k)]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+                dur_r = g2("gpu__time_duration.sum") * to_ms[u2[h2.index("gpu__time_duration.sum")]]
+                dr = {"Kernel Name": r2[h2.index("Kernel Name")]}
+            else:
+                dr, gr, dram_r, dur_r = pick("refine")
             t.update({"refine_kernel": dr["Kernel Name"].replace("void ", "").split("(")[0],
                       "refine_dram_bytes_per_launch": dram_r,
                       "refine_evals_per_launch": a.hbm_evals_refine,
