@@ -193,7 +193,8 @@ def run_mirror_e2e(sc, seeds, steps):
         env = dict(os.environ)
         env.pop("CC", None)
         env.pop("CXX", None)
-        r = subprocess.run(["g++", "-std=c++14", "-O2", "-I" + os.path.join(ROOT, "densepoints_b200", "host"),
+        r = subprocess.run(["g++", "-std=c++14", "-O2", "-fopenmp",
+                            "-I" + os.path.join(ROOT, "densepoints_b200", "host"),
                             "-I" + os.path.join(ROOT, "include"),
                             os.path.join(ROOT, "tools", "e2e_mirror_bench.cpp"), "-o", exe,
                             "-L" + os.path.dirname(lib), "-ldensepoints_cuda",
@@ -211,13 +212,17 @@ def run_mirror_e2e(sc, seeds, steps):
             f.write(np.ascontiguousarray(seeds["pos"], np.float32).tobytes())
             f.write(np.ascontiguousarray(seeds["nrm"], np.float32).tobytes())
             f.write(np.ascontiguousarray(seeds["ref"], np.int32).tobytes())
-        r = subprocess.run([exe, dump, str(CELL), str(steps)], capture_output=True, text=True, timeout=900)
+        env["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))   # (torchrun sets it to 1)
+        r = subprocess.run([exe, dump, str(CELL), str(steps)], capture_output=True, text=True, timeout=900,
+                           env=env)
         if r.returncode != 0:
             return {"error": (r.stderr or r.stdout)[-300:]}
         out = json.loads(r.stdout.strip().splitlines()[-1])
     return {"value": out["evals"] / out["seconds"], "unit": UNIT,
             "refined_patches_per_s": out["refined"] / out["seconds"], "steps": out["steps"],
             "ms_per_step": 1e3 * out["seconds"] / out["steps"],
+            "stages_ms_per_step": {k[:-2]: 1e3 * out[k] / out["steps"]
+                                   for k in ("marshal_s", "call_s", "store_s", "remove_s") if k in out},
             "what": "SeedCUDA::OptimizeAndRefinePatches() of the C++ host mirror on a "
                     "std::vector<Patch> (pageable): Patch -> SoA marshalling, dp_filter_refine, "
                     "write-back into the Patch objects, RemovePatches"}

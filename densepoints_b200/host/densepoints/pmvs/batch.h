@@ -80,28 +80,6 @@ inline std::vector<Patch *> Pointers(Patches &patches) {
   return out;
 }
 
-// Stable removal of the patches whose keep flag is 0 (Seed::RemovePatches, seed.cpp:146-156, erases
-// them one by one): destination slots from one prefix pass, then the survivors move -- and the
-// removed patches release their index vectors -- in parallel.
-inline void KeepPatches(Patches &patches, const std::vector<uint8_t> &keep) {
-  const size_t n = patches.size();
-  std::vector<size_t> dst(n);
-  size_t w = 0;
-  for (size_t i = 0; i < n; ++i) {
-    dst[i] = w;
-    w += keep[i] ? 1 : 0;
-  }
-  if (w == n) return;
-  Patches out(w);
-#pragma omp parallel for schedule(static)
-  for (long long ii = 0; ii < (long long)n; ++ii) {
-    const size_t i = (size_t)ii;
-    if (keep[i]) out[dst[i]] = std::move(patches[i]);
-    else patches[i] = Patch();
-  }
-  patches.swap(out);
-}
-
 }  // namespace PMVS
 }  // namespace DensePoints
 #endif

@@ -5,6 +5,7 @@
 #ifndef DENSEPOINTS_B200_PMVS_SEED
 #define DENSEPOINTS_B200_PMVS_SEED
 
+#include <chrono>
 #include <utility>
 #include <vector>
 
@@ -69,18 +70,36 @@ class SeedCUDA {
       ptr[i]->SetPotentiallyVisibleImages(c);
     }
   }
+  // Wall time of the stages of the last OptimizeAndRefinePatches() call, seconds: Patch -> SoA,
+  // the C-ABI call (H2D, kernels, D2H), SoA -> Patch, RemovePatches.
+  struct StageSeconds { double marshal = 0, call = 0, store = 0, remove = 0; };
+  const StageSeconds &LastStageSeconds() const { return stage_; }
+
   void OptimizeAndRefinePatches() {  // seed.cpp:88-108: FilterPatches(); OptimizePatches();
     if (patches_.empty()) return;     // one upload / download for both stages
+    typedef std::chrono::steady_clock clk;
+    const clk::time_point t0 = clk::now();
     std::vector<Patch *> ptr = Pointers(patches_);
     PatchBatch b(ptr.data(), ptr.size());
     OptimizationCUDA::WithThresholds guard(*session_, thr_, min_vis_);
     std::vector<uint8_t> keep(ptr.size());
     evals_.assign(ptr.size(), 0);
+    const clk::time_point t1 = clk::now();
     session_->Check(dp_filter_refine(session_->ctx(), &b.soa, (int)cell_size_, keep.data(), evals_.data()),
                     "dp_filter_refine");
+    const clk::time_point t2 = clk::now();
     b.StoreVisible(ptr.data());
     b.StoreGeometry(ptr.data());
-    KeepPatches(patches_, keep);  // = RemovePatches of the patches the filter dropped
+    const clk::time_point t3 = clk::now();
+    std::vector<size_t> to_remove;
+    for (size_t i = 0; i < keep.size(); ++i)
+      if (!keep[i]) to_remove.push_back(i);
+    RemovePatches(to_remove);
+    const clk::time_point t4 = clk::now();
+    stage_.marshal = std::chrono::duration<double>(t1 - t0).count();
+    stage_.call = std::chrono::duration<double>(t2 - t1).count();
+    stage_.store = std::chrono::duration<double>(t3 - t2).count();
+    stage_.remove = std::chrono::duration<double>(t4 - t3).count();
   }
   void FilterPatches() {  // seed.cpp:110-126
     if (patches_.empty()) return;
@@ -127,6 +146,7 @@ class SeedCUDA {
   size_t min_vis_;
   Patches patches_;
   std::vector<int32_t> evals_;
+  StageSeconds stage_;
 };
 
 }  // namespace PMVS

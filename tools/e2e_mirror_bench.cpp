@@ -63,7 +63,7 @@ int main(int argc, char **argv) {
     seed.GetPatches(ready);
     long long visible = 0;
     for (const Patch &p : ready) visible += (long long)p.GetTrullyVisibleImages().size();
-    double total_s = 0.0;
+    double total_s = 0.0, st_marshal = 0, st_call = 0, st_store = 0, st_remove = 0;
     long long evals = 0, refined = 0;
     for (int it = -1; it < steps; ++it) {  // it = -1: warm-up
       seed.SetPatches(ready);               // a fresh std::vector<Patch> (untimed)
@@ -72,6 +72,8 @@ int main(int argc, char **argv) {
       const auto t1 = std::chrono::steady_clock::now();
       if (it < 0) continue;
       total_s += std::chrono::duration<double>(t1 - t0).count();
+      st_marshal += seed.LastStageSeconds().marshal; st_call += seed.LastStageSeconds().call;
+      st_store += seed.LastStageSeconds().store; st_remove += seed.LastStageSeconds().remove;
       // evaluations of the step: every visible view once in the filter + evals x views of the
       // survivors (LastEvals is indexed by the patches before removal; survivors keep their order)
       const std::vector<int32_t> &ev = seed.LastEvals();
@@ -87,8 +89,9 @@ int main(int argc, char **argv) {
       evals += e;
       refined += (long long)out.size();
     }
-    std::printf("{\"steps\": %d, \"seconds\": %.6f, \"evals\": %lld, \"refined\": %lld, \"patches\": %d}\n",
-                steps, total_s, evals, refined, n);
+    std::printf("{\"steps\": %d, \"seconds\": %.6f, \"evals\": %lld, \"refined\": %lld, \"patches\": %d, "
+                "\"marshal_s\": %.6f, \"call_s\": %.6f, \"store_s\": %.6f, \"remove_s\": %.6f}\n",
+                steps, total_s, evals, refined, n, st_marshal, st_call, st_store, st_remove);
   } catch (const std::exception &e) {
     std::fprintf(stderr, "e2e_mirror_bench: %s\n", e.what());
     return 1;
