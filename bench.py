@@ -17,10 +17,13 @@ Workload (N=1): BASELINE.json configs[1] -- synthetic textured sphere, 16 views
            (+ the issue roof, from the committed ncu extract while its source hash matches)
   cpu_baseline = the CPU oracle (OpenMP, all host threads) on a bounded sample
 
-Two more legs ride on the same line (both at every N):
+Three more legs ride on the same line (all at every N):
+  c3_scoring   BASELINE configs[2] -- NCC scoring microbench, 10 M patches x 8 visible views,
+               mu = 7, on the C2 scene, the patches split evenly over the N ranks.
   expansion    BASELINE configs[3] style -- 64 views 1920x1080, 50 000 seeds (mu = 16 filter +
-               refine), Expand::ExpandPatches at mu = 11 -- with the patches sharded by reference
-               image over the N ranks and one NCCL allgather per BFS level (STRONG scaling: the
+               refine), Expand::ExpandPatches at mu = 11 -- with the frontier of every BFS level
+               cut into equal-work pieces over the N ranks (ownership by reference image is
+               timed beside it) and one NCCL allgather per level (STRONG scaling: the
                scene is fixed).  Reports refined patches/s, per-level local / allgather / commit
                times (max over ranks) and a sha256 of the final store + occupancy grids, which
                must be identical on every rank and for every N.
@@ -226,6 +229,86 @@ def run_mirror_e2e(sc, seeds, steps):
             "what": "SeedCUDA::OptimizeAndRefinePatches() of the C++ host mirror on a "
                     "std::vector<Patch> (pageable): Patch -> SoA marshalling, dp_filter_refine, "
                     "write-back into the Patch objects, RemovePatches"}
+
+
+def run_c3_leg(args, ctx, sc, rank, world, dev):
+    """BASELINE configs[2]: NCC scoring microbench, 10 M patches x 8 visible views, mu = 7, on the
+    C2 scene -- the 10 M patches are split evenly over the ranks (strong scaling, no exchange).
+    Patches are generated on the device (torch, fixed seeds) by scenes.make_seeds' rules: points on
+    the cap of the sphere the cameras face, +-1 % depth noise, inward normals tilted by a few
+    degrees, reference = nearest camera, visible set = the 8 other views nearest by angle,
+    ascending (scenes.force_visible)."""
+    import torch
+    import torch.distributed as dist
+    from densepoints_b200 import capi
+    total = 200_000 if args.small else 10_000_000
+    n = total // world
+    K = 8
+    cen = torch.from_numpy(np.ascontiguousarray(sc.centers)).to(dev)
+    pos = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    nrm = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    ref = torch.empty(n, dtype=torch.int32, device=dev)
+    vis = torch.empty((n, K), dtype=torch.int32, device=dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(3000 + rank)
+    mean_dir = cen.mean(0)
+    mean_dir = mean_dir / mean_dir.norm()
+    a = 0
+    while a < n:                       # scenes.make_seeds' rule: the cap of the sphere the cameras face
+        d = torch.randn((1 << 22, 3), generator=g, device=dev, dtype=torch.float64)
+        d /= d.norm(dim=1, keepdim=True)
+        d = d[(d @ mean_dir) > 0.80][:min(n - a, 1 << 20)]
+        m = d.shape[0]
+        b = a + m
+        r = sc.radius * (1.0 + 0.01 * (2.0 * torch.rand((m, 1), generator=g, device=dev, dtype=torch.float64) - 1.0))
+        p = d * r
+        nn = -d + 0.05 * torch.randn((m, 3), generator=g, device=dev, dtype=torch.float64)
+        nn /= nn.norm(dim=1, keepdim=True)
+        ray = p[:, None, :] - cen[None, :, :]
+        dist_c = ray.norm(dim=2)
+        rf = dist_c.argmin(dim=1)
+        cosang = ((ray / dist_c[:, :, None]) * nn[:, None, :]).sum(2)
+        cosang[torch.arange(m, device=dev), rf] = -2.0
+        idx = cosang.topk(K, dim=1).indices.sort(dim=1).values
+        pos[a:b] = p.float(); nrm[a:b] = nn.float(); ref[a:b] = rf.int(); vis[a:b] = idx.int()
+        a = b
+    nvis = torch.full((n,), K, dtype=torch.int32, device=dev)
+    ncc = torch.zeros((n, K), dtype=torch.float32, device=dev)
+    batch = capi.dev_batch(n, K, pos.data_ptr(), nrm.data_ptr(), ref.data_ptr(), nvis.data_ptr(),
+                           vis.data_ptr())
+    stream = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ctx.score_dev(batch, CELL, ncc.data_ptr(), stream=stream)        # warm-up
+    torch.cuda.synchronize()
+    reps = 3
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(2 * reps)]
+    if world > 1:
+        dist.barrier()
+    for k in range(reps):
+        flush.zero_()
+        e[2 * k].record()
+        ctx.score_dev(batch, CELL, ncc.data_ptr(), stream=stream)
+        e[2 * k + 1].record()
+    torch.cuda.synchronize()
+    ms = float(np.mean([e[2 * k].elapsed_time(e[2 * k + 1]) for k in range(reps)]))
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    ok = torch.tensor([float(torch.isfinite(ncc).all().item()), float((ncc[:, 1:] > -1).float().mean().item())],
+                      dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    ms = float(t.item())
+    evals = n * world * K
+    mean_ncc = float(ncc[:, 1:].mean().item())
+    del pos, nrm, ref, vis, nvis, ncc, flush
+    return {"workload": f"BASELINE configs[2]: NCC scoring microbench, {n * world} patches x {K} visible "
+                        f"views, mu={CELL}, C2 scene, split evenly over {world} GPU(s)",
+            "kernel": "dp_score_lane_kernel<7, 0, 0>", "ms": ms, "evals_per_s": evals / (ms * 1e-3),
+            "alg_gbs": evals * b_alg(CELL, K) / (ms * 1e-3) / 1e9,
+            "frac_hbm": evals * b_alg(CELL, K) / (ms * 1e-3) / 1e9 / hbm_peak()[0],
+            "out_bytes": n * world * K * 4, "textured_fraction": float(ok[1].item()),
+            "mean_ncc_rank0": mean_ncc, "timing": "mean of 3 launches, CUDA events, L2 flushed "
+            "between launches, max over ranks"}
 
 
 EXP_VIEWS, EXP_W, EXP_H, EXP_SEEDS, EXP_SEED_CELL, EXP_CELL, EXP_MAX_LEVELS = 64, 1920, 1080, 50_000, 16, 11, 12
@@ -664,8 +747,15 @@ def main():
         except Exception as ex:
             mirror = {"error": repr(ex)}
     launches_main = launches
-    ctx.close()
     del pos0, nrm0, ref, nvis0, vis0, pos, nrm, nvis, vis, keep, evals, flush
+    torch.cuda.empty_cache()
+    c3 = None
+    if not args.no_extra_legs:
+        try:
+            c3 = run_c3_leg(args, ctx, sc, rank, world, dev)
+        except Exception as ex:          # an extra leg must never take the bench line down
+            c3 = {"error": repr(ex)}
+    ctx.close()
     torch.cuda.empty_cache()
     expansion = hbm_leg = None
     if not args.no_extra_legs:
@@ -687,7 +777,7 @@ def main():
                         "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                         "refined_patches_per_s": e2e_refined_per_s, "cxx_mirror_pageable": mirror},
                 "gpu_launches": launches_main, "clocks": clocks, "roofline": roofline,
-                "cpu_baseline": cpu, "expansion": expansion, "roofline_hbm": hbm_leg}
+                "cpu_baseline": cpu, "c3_scoring": c3, "expansion": expansion, "roofline_hbm": hbm_leg}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
