@@ -543,7 +543,11 @@ static long long env_ll(const char *name, long long dflt) {
 // 128 / 256 evaluations for the one- / four-warp launches, thresholds 64 and 4 patches per SM):
 // one GPU 705 -> 643 ms (a stopped patch restarts at the head of the next launch, which is the
 // longest-first order the view count alone cannot give), slowest of 8 shards per level, summed,
-// 126 -> 110 ms.  DP_SLICE_B1 / _B4 / _T4 / _T8 override the knobs, DP_REFINE_SLICE=0 disables.
+// 126 -> 110 ms.  The budget is one of WORK: a patch with more than 48 visible views gets
+// budget * 48 / nvis evaluations (at least 8), so that the heavy patches of a many-view scene (C5:
+// up to 256 views) reach the multi-warp launches sooner (C5 level 1, slowest of 8 shards: 32.2 ->
+// 29.4 ms).  DP_SLICE_B1 / _B4 / _T4 / _T8 / _VIEWS override the knobs, DP_REFINE_SLICE=0 disables,
+// DP_SLICE_TRACE=1 prints one line per launch.
 // DP_REFINE_WPP=1 forces one unsliced launch with one warp per patch (A-B runs).
 template <int NPASS>
 static int refine_sliced(dp_context *ctx, DpRefineArgs a, const int32_t *nvis, cudaStream_t st) {
@@ -554,6 +558,8 @@ static int refine_sliced(dp_context *ctx, DpRefineArgs a, const int32_t *nvis, c
   const long long t4 = env_ll("DP_SLICE_T4", (long long)ctx->sm_count * 64);
   const int b1 = (int)env_ll("DP_SLICE_B1", 128), b4 = (int)env_ll("DP_SLICE_B4", 256);
   const bool slice = allow_mw && env_ll("DP_REFINE_SLICE", 1) != 0 && n > t8;
+  const bool trace = env_ll("DP_SLICE_TRACE", 0) != 0;  // per-launch lines on stderr (tuning runs)
+  a.budget_views = (int)env_ll("DP_SLICE_VIEWS", 48);
   a.n_items = (unsigned int)n;
   a.nm_save = nullptr;
   a.pending = nullptr;
@@ -583,12 +589,28 @@ static int refine_sliced(dp_context *ctx, DpRefineArgs a, const int32_t *nvis, c
     else if (m <= t4) { wpp = 4; a.budget = b4; }
     DP_CUDA(ctx, cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned int), st));
     DP_CUDA(ctx, cudaMemsetAsync(a.pending_count, 0, sizeof(unsigned int), st));
+    cudaEvent_t tr0 = nullptr, tr1 = nullptr;
+    if (trace) {
+      cudaEventCreate(&tr0);
+      cudaEventCreate(&tr1);
+      cudaEventRecord(tr0, st);
+    }
     cudaError_t ce;
     if (wpp == 8) ce = launch_refine_wpp<NPASS, 8>(a, ctx->sm_count, st);
     else if (wpp == 4) ce = launch_refine_wpp<NPASS, 4>(a, ctx->sm_count, st);
     else ce = launch_refine_wpp<NPASS, 1>(a, ctx->sm_count, st);
     ++ctx->launches;
     DP_CUDA(ctx, ce);
+    if (trace) {
+      float ms = 0.f;
+      cudaEventRecord(tr1, st);
+      cudaEventSynchronize(tr1);
+      cudaEventElapsedTime(&ms, tr0, tr1);
+      fprintf(stderr, "refine_sliced: phase %d, %lld of %lld patches, %d warp(s) per patch, budget %d: %.3f ms\n",
+              phase, m, n, wpp, a.budget, ms);
+      cudaEventDestroy(tr0);
+      cudaEventDestroy(tr1);
+    }
     if (a.budget == 0) break;
     unsigned int left = 0;
     DP_CUDA(ctx, cudaMemcpyAsync(&left, a.pending_count, sizeof(left), cudaMemcpyDeviceToHost, st));
@@ -674,6 +696,7 @@ extern "C" int dp_refine_dev(dp_context *ctx, dp_patch_dev *p, int cell_size, co
   a.pending = nullptr;
   a.pending_count = nullptr;
   a.budget = 0;
+  a.budget_views = 0;
   a.resume = 0;
 #ifdef DP_DEBUG_TRACE
   {

@@ -239,6 +239,8 @@ struct DpRefineArgs {
   uint8_t *pending;            // n flags, written by every launch: 1 = stopped, to be continued
   unsigned int *pending_count; // number of patches this launch left pending (zeroed before)
   int budget;                  // evaluations per patch in this launch; 0 = unlimited
+  int budget_views;            // a patch with more visible views than this gets budget * budget_views / nvis
+                               // evaluations (>= 8): the budget is one of WORK, heavy patches move on sooner
   int resume;                  // 1: the patches with mask != 0 continue from nm_save
   unsigned int n_items;        // work items dp_refine_kernel hands out (<= n; the first entries of order)
 #ifdef DP_DEBUG_TRACE
@@ -471,9 +473,12 @@ __global__ void __launch_bounds__(DP_RWARPS * 32, dp_refine_min_ctas(NPASS)) dp_
       __syncwarp();
     }
     int spent = 0;  // objective evaluations of this patch in this launch
+    const int budget = (a.budget > 0 && a.budget_views > 0 && nv > a.budget_views)
+                           ? max(8, (int)(((long long)a.budget * a.budget_views) / nv))
+                           : a.budget;
 #pragma unroll 1
     for (;;) {
-      if (a.budget > 0 && spent >= a.budget && state != ST_DONE) {
+      if (budget > 0 && spent >= budget && state != ST_DONE) {
         // out of budget: the state goes to global memory as it is, S.pt is the next point
         __syncwarp();
         if (wg == 0) {

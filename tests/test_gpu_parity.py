@@ -196,6 +196,7 @@ def test_refine_vs_oracle(c1, exact_orc, s, n, refine_kernel):
 
 @pytest.mark.parametrize("s,knobs", [
     (11, dict(DP_SLICE_T8="10", DP_SLICE_T4="100", DP_SLICE_B1="7", DP_SLICE_B4="9")),   # 1 -> 4 -> 8 warps
+    (11, dict(DP_SLICE_T8="10", DP_SLICE_T4="100", DP_SLICE_B1="40", DP_SLICE_B4="60", DP_SLICE_VIEWS="1")),  # budget scaled by the view count
     (11, dict(DP_SLICE_T8="1", DP_SLICE_T4="1", DP_SLICE_B1="5")),                       # many 1-warp slices
     (16, dict(DP_SLICE_T8="1", DP_SLICE_T4="100000", DP_SLICE_B4="6")),                  # 4-warp slices only
     (20, dict(DP_SLICE_T8="200", DP_SLICE_T4="300", DP_SLICE_B1="16", DP_SLICE_B4="16")),

@@ -14,13 +14,26 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--world", type=int, default=8)
 ap.add_argument("--levels", type=int, default=12)
 ap.add_argument("--out", default="")
+ap.add_argument("--c5", action="store_true", help="the C5 scene (256 views 3840x2160, 200 000 seeds) instead")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
-sc = scenes.make_plane_scene(seed=4, n_views=64, width=1920, height=1080, yaw_spread_deg=25.0,
-                             name="C4", device="cuda:0")
-seeds = scenes.make_seeds(sc, 50_000, seed=40, depth_noise=0.003, tilt_deg=5.0)
-ctx = capi.Context(0)
-ctx.set_views(sc.P, sc.images)
+if a.c5:
+    W, H = 3840, 2160
+    P, centers, Rs, f, cx, cy, extent, tex = scenes.lattice_plane_cameras(nx=16, ny=16, width=W, height_px=H, f=3000.0)
+    ctx = capi.Context(0)
+    ctx.set_num_views(len(P))
+    for v in range(len(P)):
+        img = scenes.render_plane_view(centers[v], Rs[v], f, cx, cy, W, H, extent, tex, dev)
+        ctx.upload_view(v, P[v], img)
+    sc = scenes.Scene("C5", P, [np.zeros((1, 1, 3), np.uint8)] * len(P), W, H, "plane", extent=extent, centers=centers)
+    sc.extent = 0.5 * 15 * 4.0 / 0.8
+    seeds = scenes.make_seeds(sc, 200_000, seed=50, depth_noise=0.003, tilt_deg=5.0)
+else:
+    sc = scenes.make_plane_scene(seed=4, n_views=64, width=1920, height=1080, yaw_spread_deg=25.0,
+                                 name="C4", device="cuda:0")
+    seeds = scenes.make_seeds(sc, 50_000, seed=40, depth_noise=0.003, tilt_deg=5.0)
+    ctx = capi.Context(0)
+    ctx.set_views(sc.P, sc.images)
 nvis, vis, _, _ = ctx.visibility(seeds["pos"], seeds["nrm"], seeds["ref"])
 keep, fnvis, fvis, pos, nrm, evs = ctx.filter_refine(seeds["pos"], seeds["nrm"], seeds["ref"], nvis, vis, 16)
 m = keep.astype(bool)
