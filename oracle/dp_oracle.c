@@ -50,7 +50,16 @@ void orc_default_params(orc_params *p) {
 
 /* ------------------------------------------------------------------------ */
 /* small vector helpers                                                      */
+/* Evaluation order of Eigen's small fixed-size sums: 0 = sequential
+ * ((a0+a1)+a2)+a3, what Eigen 3.2's unrolled coefficient products do and what the oracle and the
+ * kernels assume; 1 = the halving order of Eigen >= 3.3's redux unroller, (a0+a1)+(a2+a3) for four
+ * terms and a0+(a1+a2) for three.  Mode 1 exists to MEASURE what the unpinned Eigen version can
+ * change (tests/test_oracle_logic.py); the product path is mode 0. */
+static int g_eigen_pairwise = 0;
+void orc_set_eigen_pairwise(int on) { g_eigen_pairwise = on; }
+
 static double dot3(const double a[3], const double b[3]) {
+  if (g_eigen_pairwise) return a[0] * b[0] + (a[1] * b[1] + a[2] * b[2]);
   return a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
 }
 static double norm3(const double a[3]) { return sqrt(dot3(a, a)); }
@@ -121,9 +130,16 @@ void orc_view_init(orc_view *v, const double P[12], const uint8_t *bgr, int widt
 /* View::ProjectPoint (types.cpp:70-75) */
 void orc_project(const orc_view *v, const double X[3], double uv[2]) {
   const double *P = v->P;
-  double x = P[0] * X[0] + P[1] * X[1] + P[2] * X[2] + P[3];
-  double y = P[4] * X[0] + P[5] * X[1] + P[6] * X[2] + P[7];
-  double w = P[8] * X[0] + P[9] * X[1] + P[10] * X[2] + P[11];
+  double x, y, w;
+  if (g_eigen_pairwise) {
+    x = (P[0] * X[0] + P[1] * X[1]) + (P[2] * X[2] + P[3]);
+    y = (P[4] * X[0] + P[5] * X[1]) + (P[6] * X[2] + P[7]);
+    w = (P[8] * X[0] + P[9] * X[1]) + (P[10] * X[2] + P[11]);
+  } else {
+    x = P[0] * X[0] + P[1] * X[1] + P[2] * X[2] + P[3];
+    y = P[4] * X[0] + P[5] * X[1] + P[6] * X[2] + P[7];
+    w = P[8] * X[0] + P[9] * X[1] + P[10] * X[2] + P[11];
+  }
   uv[0] = x / w;
   uv[1] = y / w;
 }

@@ -60,6 +60,9 @@ typedef struct orc_params {
 } orc_params;
 
 void orc_default_params(orc_params *p);
+/* 0 (default): sums in sequential order (Eigen 3.2); 1: Eigen >= 3.3's halving order -- a
+ * measuring device for the unpinned Eigen version, see dp_oracle.c */
+void orc_set_eigen_pairwise(int on);
 
 /* Per-(patch, view) pyramid level (see dp_oracle.c): levels = [n_levels][n_views] view tables,
  * level 0 first (must be the array later calls pass as `views`); NULL or n_levels <= 1 = off. */

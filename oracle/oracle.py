@@ -401,6 +401,20 @@ def levels_batch(views, pos, nrm, ref, nvis, vis, cell_size):
     return out
 
 
+def project(views: Views, view_id, X):
+    """View::ProjectPoint (types.cpp:70-75)."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    uv = np.zeros(2)
+    lib().orc_project(C.byref(views.arr[int(view_id)]), _p(X), _p(uv))
+    return uv
+
+
+def set_eigen_pairwise(on: bool):
+    """Sum order of Eigen's small fixed-size products: False = sequential (Eigen 3.2, the
+    default everywhere), True = the halving order of Eigen >= 3.3 (a measuring device)."""
+    lib().orc_set_eigen_pairwise(C.c_int(1 if on else 0))
+
+
 def set_homography_mode(mode: int):
     """0 = OpenCV's DLT + eigen-solve + inversion (pinned against cv2); 1 = exact closed form
     (deterministic at ties; what the CUDA path is checked against).  See dp_oracle.h."""
