@@ -87,7 +87,7 @@ class OracleLevelBackend:
         return self.org.size() - n0
 
 
-def _worker(rank, world, port, outdir, balance):
+def _worker(rank, world, port, outdir, balance, m=1):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle import oracle as orc
@@ -98,7 +98,7 @@ def _worker(rank, world, port, outdir, balance):
     full, _ = _scene()
     assert all(np.array_equal(a, b) for a, b in zip(sc.images, full.images))
     V = orc.Views(sc.P, sc.images)
-    prm = orc.default_params(minimum_visible_image=2)
+    prm = orc.default_params(minimum_visible_image=2, max_patches_per_cell=m)
     nvis, vis, _, _ = orc.visibility_batch(V, seeds["pos"], seeds["nrm"], seeds["ref"])
     be = OracleLevelBackend(orc, V, prm, seeds, nvis, vis)
     # fixed contiguous ownership, or re-balanced every level from the frontier (assign_views)
@@ -134,11 +134,12 @@ def test_assign_views_is_deterministic_and_balanced():
     assert (dd.assign_views(w, 1) == 0).all()
 
 
-@pytest.mark.parametrize("world,balance", [(2, 0), (3, 0), (2, 1), (3, 1), (2, 2), (3, 2)])
-def test_multi_rank_expansion_matches_single_process_fifo(orc, world, balance):
+@pytest.mark.parametrize("world,balance,m", [(2, 0, 1), (3, 0, 1), (2, 1, 1), (3, 1, 1), (2, 2, 1), (3, 2, 1),
+                                             (2, 2, 2)])     # m: max_patches_per_cell
+def test_multi_rank_expansion_matches_single_process_fifo(orc, world, balance, m):
     sc, seeds = _scene()
     V = orc.Views(sc.P, sc.images)
-    prm = orc.default_params(minimum_visible_image=2)
+    prm = orc.default_params(minimum_visible_image=2, max_patches_per_cell=m)
     nvis, vis, _, _ = orc.visibility_batch(V, seeds["pos"], seeds["nrm"], seeds["ref"])
     ref_org = orc.Organizer(V, prm)
     ref_org.set_seeds(seeds["pos"], seeds["nrm"], seeds["ref"], nvis, vis)
@@ -148,7 +149,7 @@ def test_multi_rank_expansion_matches_single_process_fifo(orc, world, balance):
     assert ref_org.size() > n_seed
     with tempfile.TemporaryDirectory() as d:
         port = 29500 + (os.getpid() % 2000)
-        mp.spawn(_worker, args=(world, port + world + 10 * int(balance), d, balance), nprocs=world,
+        mp.spawn(_worker, args=(world, port + world + 10 * int(balance) + 40 * (m - 1), d, balance, m), nprocs=world,
                  join=True)
         got = [dict(np.load(os.path.join(d, f"rank{r}.npz"))) for r in range(world)]
     grids = np.concatenate([ref_org.grid(v).ravel() for v in range(sc.n_views)])
