@@ -17,9 +17,27 @@ struct ExpandOptions {
   ExpandOptions(size_t cell_size = 11) : cell_size(cell_size) {}
 };
 
+// patch_organizer.h:40-47
+struct PatchOrganizerOptions {
+  size_t max_patches_per_cell;
+  size_t grid_scale;
+  PatchOrganizerOptions(size_t max_patches_per_cell = 1, size_t grid_scale = 8)
+      : max_patches_per_cell(max_patches_per_cell), grid_scale(grid_scale) {}
+};
+
 class Expand {
  public:
   Expand(Session session, ExpandOptions options = ExpandOptions()) : session_(session), options_(options) {}
+  void SetOptions(const ExpandOptions expand_options) { options_ = expand_options; }
+  // The reference's Expand::SetSeeds builds its PatchOrganizer with default options
+  // (expand.cpp:16); PatchOrganizer::SetOptions (patch_organizer.h:56-58) is how a caller changes
+  // them.  Here they travel in dp_params; call before SetSeeds.
+  void SetOrganizerOptions(const PatchOrganizerOptions o) {
+    dp_params p = session_->Params();
+    p.max_patches_per_cell = (int32_t)o.max_patches_per_cell;
+    p.grid_scale = (int32_t)o.grid_scale;
+    session_->SetParams(p);
+  }
 
   // expand.cpp:13-32: new organizer, AllocateViews, SetSeeds, ExpandPatches
   void SetSeeds(const Patches seeds, int max_levels = -1) {
