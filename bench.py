@@ -231,36 +231,33 @@ def run_mirror_e2e(sc, seeds, steps):
                     "write-back into the Patch objects, RemovePatches"}
 
 
-def run_c3_leg(args, ctx, sc, rank, world, dev):
-    """BASELINE configs[2]: NCC scoring microbench, 10 M patches x 8 visible views, mu = 7, on the
-    C2 scene -- the 10 M patches are split evenly over the ranks (strong scaling, no exchange).
-    Patches are generated on the device (torch, fixed seeds) by scenes.make_seeds' rules: points on
-    the cap of the sphere the cameras face, +-1 % depth noise, inward normals tilted by a few
-    degrees, reference = nearest camera, visible set = the 8 other views nearest by angle,
-    ascending (scenes.force_visible)."""
+def c3_patches(centers, radius, n, seed, dev, K=8):
+    """The C3 microbench's patches, generated with torch on `dev` by scenes.make_seeds' rules:
+    points on the cap of the sphere the cameras face (d . mean camera direction > 0.8), +-1 % depth
+    noise, inward normals tilted by a few degrees, reference = nearest camera, visible set = the K
+    other views nearest by angle, ascending (scenes.force_visible).  Returns pos, nrm (n x 3
+    float32), ref (n int32), vis (n x K int32)."""
     import torch
-    import torch.distributed as dist
-    from densepoints_b200 import capi
-    total = 200_000 if args.small else 10_000_000
-    n = total // world
-    K = 8
-    cen = torch.from_numpy(np.ascontiguousarray(sc.centers)).to(dev)
+    cen = torch.from_numpy(np.ascontiguousarray(centers)).to(dev)
     pos = torch.empty((n, 3), dtype=torch.float32, device=dev)
     nrm = torch.empty((n, 3), dtype=torch.float32, device=dev)
     ref = torch.empty(n, dtype=torch.int32, device=dev)
     vis = torch.empty((n, K), dtype=torch.int32, device=dev)
     g = torch.Generator(device=dev)
-    g.manual_seed(3000 + rank)
+    g.manual_seed(seed)
     mean_dir = cen.mean(0)
     mean_dir = mean_dir / mean_dir.norm()
+    draw = min(1 << 22, max(4096, 16 * n))
     a = 0
-    while a < n:                       # scenes.make_seeds' rule: the cap of the sphere the cameras face
-        d = torch.randn((1 << 22, 3), generator=g, device=dev, dtype=torch.float64)
+    while a < n:
+        d = torch.randn((draw, 3), generator=g, device=dev, dtype=torch.float64)
         d /= d.norm(dim=1, keepdim=True)
         d = d[(d @ mean_dir) > 0.80][:min(n - a, 1 << 20)]
         m = d.shape[0]
+        if m == 0:
+            continue
         b = a + m
-        r = sc.radius * (1.0 + 0.01 * (2.0 * torch.rand((m, 1), generator=g, device=dev, dtype=torch.float64) - 1.0))
+        r = radius * (1.0 + 0.01 * (2.0 * torch.rand((m, 1), generator=g, device=dev, dtype=torch.float64) - 1.0))
         p = d * r
         nn = -d + 0.05 * torch.randn((m, 3), generator=g, device=dev, dtype=torch.float64)
         nn /= nn.norm(dim=1, keepdim=True)
@@ -272,42 +269,61 @@ def run_c3_leg(args, ctx, sc, rank, world, dev):
         idx = cosang.topk(K, dim=1).indices.sort(dim=1).values
         pos[a:b] = p.float(); nrm[a:b] = nn.float(); ref[a:b] = rf.int(); vis[a:b] = idx.int()
         a = b
-    nvis = torch.full((n,), K, dtype=torch.int32, device=dev)
-    ncc = torch.zeros((n, K), dtype=torch.float32, device=dev)
-    batch = capi.dev_batch(n, K, pos.data_ptr(), nrm.data_ptr(), ref.data_ptr(), nvis.data_ptr(),
-                           vis.data_ptr())
-    stream = torch.cuda.current_stream().cuda_stream
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    ctx.score_dev(batch, CELL, ncc.data_ptr(), stream=stream)        # warm-up
-    torch.cuda.synchronize()
-    reps = 3
-    e = [torch.cuda.Event(enable_timing=True) for _ in range(2 * reps)]
-    if world > 1:
-        dist.barrier()
-    for k in range(reps):
-        flush.zero_()
-        e[2 * k].record()
-        ctx.score_dev(batch, CELL, ncc.data_ptr(), stream=stream)
-        e[2 * k + 1].record()
-    torch.cuda.synchronize()
-    ms = float(np.mean([e[2 * k].elapsed_time(e[2 * k + 1]) for k in range(reps)]))
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    ok = torch.tensor([float(torch.isfinite(ncc).all().item()), float((ncc[:, 1:] > -1).float().mean().item())],
-                      dtype=torch.float64, device=dev)
+    return pos, nrm, ref, vis
+
+
+def run_c3_leg(args, ctx, sc, rank, world, dev):
+    """BASELINE configs[2]: NCC scoring microbench, 10 M patches x 8 visible views, mu = 7, on the
+    C2 scene -- the 10 M patches are split evenly over the ranks (strong scaling, no exchange).
+    The local work runs under a try; the two reductions after it are reached by every rank
+    whatever happened, so a failure on one rank cannot leave the others waiting."""
+    import torch
+    import torch.distributed as dist
+    from densepoints_b200 import capi
+    total = 200_000 if args.small else 10_000_000
+    n = total // world
+    K = 8
+    ms, textured, mean_ncc, err = float("nan"), 0.0, float("nan"), None
+    try:
+        pos, nrm, ref, vis = c3_patches(sc.centers, sc.radius, n, 3000 + rank, dev, K)
+        nvis = torch.full((n,), K, dtype=torch.int32, device=dev)
+        ncc = torch.zeros((n, K), dtype=torch.float32, device=dev)
+        batch = capi.dev_batch(n, K, pos.data_ptr(), nrm.data_ptr(), ref.data_ptr(), nvis.data_ptr(),
+                               vis.data_ptr())
+        stream = torch.cuda.current_stream().cuda_stream
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        ctx.score_dev(batch, CELL, ncc.data_ptr(), stream=stream)        # warm-up
+        torch.cuda.synchronize()
+        reps = 3
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(2 * reps)]
+        for k in range(reps):
+            flush.zero_()
+            e[2 * k].record()
+            ctx.score_dev(batch, CELL, ncc.data_ptr(), stream=stream)
+            e[2 * k + 1].record()
+        torch.cuda.synchronize()
+        ms = float(np.mean([e[2 * k].elapsed_time(e[2 * k + 1]) for k in range(reps)]))
+        textured = float((ncc[:, 1:] > -1).float().mean().item()) if bool(torch.isfinite(ncc).all().item()) else 0.0
+        mean_ncc = float(ncc[:, 1:].mean().item())
+        del pos, nrm, ref, vis, nvis, ncc, flush
+    except Exception as ex:
+        err = repr(ex)
+    t = torch.tensor([ms if ms == ms else 1e30], dtype=torch.float64, device=dev)
+    ok = torch.tensor([textured], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     ms = float(t.item())
+    if err is not None or ms >= 1e29:
+        return {"error": err or "a rank failed"}
     evals = n * world * K
-    mean_ncc = float(ncc[:, 1:].mean().item())
-    del pos, nrm, ref, vis, nvis, ncc, flush
     return {"workload": f"BASELINE configs[2]: NCC scoring microbench, {n * world} patches x {K} visible "
                         f"views, mu={CELL}, C2 scene, split evenly over {world} GPU(s)",
             "kernel": "dp_score_lane_kernel<7, 0, 0>", "ms": ms, "evals_per_s": evals / (ms * 1e-3),
             "alg_gbs": evals * b_alg(CELL, K) / (ms * 1e-3) / 1e9,
             "frac_hbm": evals * b_alg(CELL, K) / (ms * 1e-3) / 1e9 / hbm_peak()[0],
-            "out_bytes": n * world * K * 4, "textured_fraction": float(ok[1].item()),
-            "mean_ncc_rank0": mean_ncc, "timing": "mean of 3 launches, CUDA events, L2 flushed "
+            "out_bytes": n * world * K * 4, "textured_fraction": float(ok.item()),
+            "mean_ncc_rank0": mean_ncc, "timing": "mean of 3 launches per rank, CUDA events, L2 flushed "
             "between launches, max over ranks"}
 
 
