@@ -279,3 +279,40 @@ def test_eigen_sum_order_sensitivity(orc):
     assert np.abs(a["ncc"] - b["ncc"]).max() == 0
     print(f"Eigen sum order: max |d projection| {duv.max():.2e} px over {len(duv)} points, "
           f"{(duv > 0).sum()} coordinates differ in the last bits; {a['valid'].sum()} textures identical")
+
+
+@pytest.mark.parametrize("m", [1, 2, 3])
+def test_set_seeds_against_a_direct_restatement(orc, m):
+    """PatchOrganizer::SetSeeds / TryInsert / PatchGrid::TryInsert (patch_organizer.cpp:15-75)
+    restated line by line in Python -- cells as lists with a capacity of max_patches_per_cell,
+    a patch kept iff it entered more than one cell, cells consumed either way --
+    against the oracle's organizer, for 1, 2 and 3 patches per cell on seeds dense enough to
+    fill cells."""
+    sc = scenes.make_plane_scene(seed=5, n_views=4, width=160, height=120, yaw_spread_deg=14.0)
+    seeds = scenes.make_seeds(sc, 700, seed=6, depth_noise=0.004, tilt_deg=4.0)
+    V = orc.Views(sc.P, sc.images)
+    nvis, vis, _, _ = orc.visibility_batch(V, seeds["pos"], seeds["nrm"], seeds["ref"])
+    prm = orc.default_params(minimum_visible_image=2, max_patches_per_cell=m)
+    org = orc.Organizer(V, prm)
+    acc = org.set_seeds(seeds["pos"], seeds["nrm"], seeds["ref"], nvis, vis)
+    gs = 8
+    gw, gh = 160 // gs, 120 // gs                                  # AllocateViews, :32-40
+    grids = [[[0] * gw for _ in range(gh)] for _ in range(sc.n_views)]
+    want = []
+    for i in range(len(nvis)):
+        cells = 0
+        for v in vis[i, :nvis[i]]:
+            uv = orc.project(V, int(v), seeds["pos"][i].astype(np.float64))     # :46
+            qr, qc = uv[1] / gs, uv[0] / gs
+            if not (qr > -1 and qc > -1):                         # static_cast<size_t> of q <= -1: out of bounds
+                continue
+            row, col = int(qr), int(qc)                           # :47-48 (truncation toward zero)
+            if col < gw and row < gh and grids[v][row][col] < m:  # PatchGrid::TryInsert, :18-26
+                grids[v][row][col] += 1
+                cells += 1
+        want.append(1 if cells > 1 else 0)                        # :58
+    assert np.array_equal(acc, np.array(want, acc.dtype))
+    for v in range(sc.n_views):
+        assert np.array_equal(org.grid(v), np.array(grids[v], np.uint8))
+    assert max(max(max(r) for r in g) for g in grids) == m        # cells did fill up
+    assert org.size() == sum(want)
