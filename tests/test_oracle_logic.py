@@ -316,3 +316,42 @@ def test_set_seeds_against_a_direct_restatement(orc, m):
         assert np.array_equal(org.grid(v), np.array(grids[v], np.uint8))
     assert max(max(max(r) for r in g) for g in grids) == m        # cells did fill up
     assert org.size() == sum(want)
+
+
+def test_init_related_images_against_a_direct_restatement(orc):
+    """Patch::InitRelatedImages (patch.cpp:19-49) restated in Python doubles -- reference view
+    skipped, strict IsPointInside (types.cpp:77-84), angle = acos(n . d / |d|) with d = position -
+    camera centre, < 0.78 -> visible, < 1.04 -> candidate, ascending view order -- against the
+    oracle, bit for bit, on a 16-view scene (the visible sets are an integer output north_star
+    wants bit-exact; the CUDA kernel is compared with the oracle on the GPU)."""
+    import math
+    sc = scenes.make_sphere_scene(seed=2, n_views=16, width=160, height=120, f=125.0)
+    seeds = scenes.make_seeds(sc, 1500, seed=21)
+    V = orc.Views(sc.P, sc.images)
+    nvis, vis, ncand, cand = orc.visibility_batch(V, seeds["pos"], seeds["nrm"], seeds["ref"])
+    C = [V.center(i) for i in range(sc.n_views)]
+    seen_vis = seen_cand = 0
+    for i in range(len(nvis)):
+        n = [float(x) for x in seeds["nrm"][i]]                   # fp32 storage -> double (patch.h:38-53)
+        p = [float(x) for x in seeds["pos"][i]]
+        wv, wc = [], []
+        for v in range(sc.n_views):
+            if v == seeds["ref"][i]:
+                continue
+            uv = orc.project(V, v, np.array(p))
+            if not (uv[0] > 0 and uv[0] < 160 and uv[1] > 0 and uv[1] < 120):
+                continue
+            d = [p[0] - C[v][0], p[1] - C[v][1], p[2] - C[v][2]]
+            dot = n[0] * d[0] + n[1] * d[1] + n[2] * d[2]
+            nd = math.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2])
+            q = dot / nd
+            angle = math.acos(q) if -1.0 <= q <= 1.0 else float("nan")
+            if angle < 0.78:
+                wv.append(v)
+            elif angle < 1.04:
+                wc.append(v)
+        assert list(vis[i, :nvis[i]]) == wv and nvis[i] == len(wv), i
+        assert list(cand[i, :ncand[i]]) == wc and ncand[i] == len(wc), i
+        seen_vis += len(wv)
+        seen_cand += len(wc)
+    assert seen_vis > 3000 and seen_cand > 100
